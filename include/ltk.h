@@ -1,0 +1,126 @@
+/* ltk.h -- C ABI of the B200-native batched lap-time kernels ("ltk").
+ *
+ * Drop-in boundary for the one data-parallel hot path of bruno-maruszczak/lap-time-optimization:
+ * scoring candidate racing lines (alpha vectors) to lap times.  The reference has no FFI of its own --
+ * its boundary is the Python class surface Path / VelocityProfile / Trajectory.lap_time /
+ * TrajectoryBayesianNonlinear.calcMinTime -- so each entry point below names the reference lines it
+ * replaces (paths relative to the reference's src/).  The Python facade in
+ * lap_time_optimization_b200/ binds these with ctypes; INTEGRATION.md shows the stub a maintainer
+ * of the reference would add.
+ *
+ * Conventions
+ *   - plain C types only; every array argument named d_* is a CALLER-OWNED DEVICE pointer (e.g.
+ *     torch.Tensor.data_ptr()); h_* are host pointers read during the call only.  Nothing is retained
+ *     or freed by the library except what ltk_create allocates inside the context.
+ *   - work is enqueued on the caller's stream (`stream` is a cudaStream_t passed as void*; NULL = the
+ *     legacy default stream) and the call returns without synchronising unless stated.
+ *   - return value: 0 = OK, negative = error (LTK_E_*); ltk_last_error(ctx) gives the message.
+ *   - a context is bound to one device; contexts are not thread-safe; no exceptions cross the ABI.
+ *   - arithmetic is IEEE fp64 throughout (no fast-math); there is no CPU fallback.
+ */
+#ifndef LTK_H
+#define LTK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LTK_MAX_ENGINE_MAP 16
+
+#define LTK_OK 0
+#define LTK_E_ARG -1       /* bad argument */
+#define LTK_E_CUDA -2      /* CUDA runtime error (see ltk_last_error) */
+#define LTK_E_WORKSPACE -3 /* workspace too small */
+#define LTK_E_UNSUPPORTED -4
+
+/* Vehicle constants, pre-folded on the host in the reference's own operation order.
+ * kind 0: tabulated engine map -- reference vehicle.py:11-35 (TBR18)
+ * kind 1: polynomial engine    -- reference vehicleMX5.py:19-37 (MX-5)                      */
+typedef struct ltk_vehicle {
+    int32_t kind;
+    int32_t n_map;                       /* kind 0: number of engine-map nodes (2..16) */
+    double mass;                         /* vehicle.py:16 / vehicleMX5.py:54 */
+    double mu_g;                         /* friction_coef * 9.81          (velocity.py:29) */
+    double f_max;                        /* (mu*m)*g  (vehicle.py:30)  |  (lam*D)*(m*g) (vehicleMX5.py:28-33) */
+    double f_max_sq;                     /* f_max**2 */
+    double map_v[LTK_MAX_ENGINE_MAP];    /* engineMap.v, ascending (vehicle.py:18-21) */
+    double map_f[LTK_MAX_ENGINE_MAP];    /* engineMap.f */
+    double e0;                           /* kind 1: (T*C_m) - Cr_0        (vehicleMX5.py:21) */
+    double cr2;                          /* kind 1: Cr_2 */
+} ltk_vehicle;
+
+typedef struct ltk_ctx ltk_ctx;
+
+/* Create an evaluator for one (track, vehicle, sampling) triple.
+ *   h_left_xy, h_diff_xy : [2][n_ctrl] row-major (x row, y row) -- inner boundary point and
+ *       inner->outer vector of each UNIQUE control point (the closing duplicate is implied).
+ *       Replaces the constants behind Track.control_points / control_points_bayesian
+ *       (track.py:82-94) including the closure quirk of trajectory_bayesian_nonlinear.py:58-69.
+ *   ns : samples per lap including the end point (Trajectory.ns, trajectory.py:35); ns-1 are swept.
+ *   Only closed tracks are supported by the batched path (all four reference tracks are closed). */
+int ltk_create(ltk_ctx **out, int device, const double *h_left_xy, const double *h_diff_xy,
+               int n_ctrl, const ltk_vehicle *vehicle, int ns);
+void ltk_destroy(ltk_ctx *ctx);
+const char *ltk_last_error(const ltk_ctx *ctx); /* ctx may be NULL: last creation error */
+
+/* Change the sampling density (Trajectory.ns is a plain attribute in the reference). */
+int ltk_set_ns(ltk_ctx *ctx, int ns);
+
+/* Bytes of device scratch ltk_eval_* needs for a batch of B candidates. */
+int ltk_workspace_bytes(const ltk_ctx *ctx, int64_t B, size_t *out_bytes);
+
+/* alphas -> lap times.  d_alphas [B][n_ctrl] row-major fp64, d_lap [B].
+ * Replaces, per candidate: TrajectoryBayesianNonlinear.calcMinTime(updateAlphas(a))
+ * (trajectory_bayesian_nonlinear.py:58-80) and Trajectory.update/update_velocity/lap_time
+ * (trajectory.py:40-58): Track.control_points* (track.py:82-94), Path.__init__ (path.py:20-26),
+ * np.linspace sampling, Path.curvature (path.py:36-61), VelocityProfile (velocity.py:14-76),
+ * Vehicle.engine_force/traction (vehicle.py:25-35, vehicleMX5.py:19-37), lap_time (:51-54).
+ * Kernels launched: K1 spline+curvature, K2 forward sweep, K3 backward sweep + lap reduction. */
+int ltk_eval_alphas(ltk_ctx *ctx, const double *d_alphas, int64_t B, double *d_lap,
+                    void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* control points -> lap times: the calcMinTime(controls) surface
+ * (trajectory_bayesian_nonlinear.py:65-80).  d_xy [B][2][m] row-major with m = n_ctrl + 1 columns
+ * (the last column is the closing duplicate and is ignored, exactly as splprep(per=1) overwrites it). */
+int ltk_eval_controls(ltk_ctx *ctx, const double *d_xy, int m, int64_t B, double *d_lap,
+                      void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* Full profile of ONE candidate in natural sample order, for the facade attributes
+ * (VelocityProfile.v / v_local / v_acclim / v_declim, Trajectory.s; velocity.py:20-26).
+ * Each output is a device array of ns-1 doubles (d_s: ns doubles) and may be NULL; d_scalars[2] =
+ * {lap time, path length}.  Synchronises the stream. */
+int ltk_profile(ltk_ctx *ctx, const double *d_alpha, double *d_s, double *d_k, double *d_vlocal,
+                double *d_vacc, double *d_vdec, double *d_v, double *d_scalars, void *stream);
+
+/* Stable ascending top-k of lap times: what `sorted(zip(taus, alphas), key=tau)[0:10]` selects
+ * (trajectory_bayesian_nonlinear.py:253-257).  Ties keep the lower index; NaN sorts last.
+ * d_best_idx holds index_base + position.  k <= 64. */
+int ltk_topk(ltk_ctx *ctx, const double *d_lap, int64_t B, int64_t index_base, int k,
+             double *d_best_lap, int64_t *d_best_idx, void *stream);
+
+/* Path facade (path.py:17-77): evaluate the periodic spline through m-1 unique points
+ * d_xy [2][m] (closed; last column ignored) with knots d_knots [m] (Path.dists) at n parameters d_u.
+ * Any of the outputs may be NULL. d_gamma2[1] receives sum(k^2) (path.py:63-77). */
+int ltk_path_eval(int device, const double *d_xy, const double *d_knots, int m, const double *d_u,
+                  int64_t n, double *d_x, double *d_y, double *d_dx, double *d_dy, double *d_ddx,
+                  double *d_ddy, double *d_k_signed, double *d_gamma2, void *stream);
+
+/* VelocityProfile facade (velocity.py:9-76) for caller-supplied samples: d_s, d_k [n];
+ * s_max < 0 means an open path (s_max=None in the reference). Outputs [n] each; d_vacc and d_vdec are
+ * required (they are the sweep state), d_vlocal and d_v may be NULL. */
+int ltk_velocity_profile(int device, const ltk_vehicle *vehicle, const double *d_s, const double *d_k,
+                         int64_t n, double s_max, double *d_vlocal, double *d_vacc, double *d_vdec,
+                         double *d_v, void *stream);
+
+/* Library/ABI version and a count of kernel launches issued through this library since load
+ * (bench.py reports it as gpu_launches). */
+int ltk_version(void);
+int64_t ltk_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LTK_H */

@@ -1,0 +1,410 @@
+// ltk_api.cu -- C ABI (include/ltk.h) over the kernels in ltk_kernels.cuh.  sm_100a only.
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "ltk_kernels.cuh"
+
+using namespace ltk;
+
+static std::atomic<long long> g_launches{0};
+static char g_create_err[256] = "";
+
+struct ltk_ctx {
+    int device;
+    int N, ns;
+    int sm_count;
+    size_t smem_optin;
+    double* d_left;  // [2][N]
+    double* d_diff;  // [2][N]
+    VehDev veh;
+    // scratch owned by the context
+    double* d_topk_lap;
+    long long* d_topk_idx;
+    void* d_profile_ws;
+    size_t profile_ws_bytes;
+    int k1_g_override, k1_staged_override;
+    char err[256];
+};
+
+namespace {
+
+constexpr int TOPK_MAX_BLOCKS = 296;
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev)
+    {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+int fail(ltk_ctx* ctx, int code, const char* what, cudaError_t e = cudaSuccess)
+{
+    char* dst = ctx ? ctx->err : g_create_err;
+    if (e != cudaSuccess) snprintf(dst, 256, "%s: %s", what, cudaGetErrorString(e));
+    else snprintf(dst, 256, "%s", what);
+    return code;
+}
+
+#define LTK_CUDA(ctx, call)                                                   \
+    do {                                                                      \
+        cudaError_t e_ = (call);                                              \
+        if (e_ != cudaSuccess) return fail(ctx, LTK_E_CUDA, #call, e_);       \
+    } while (0)
+
+inline long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
+
+VehDev make_vehdev(const ltk_vehicle& v)
+{
+    VehDev d;
+    memset(&d, 0, sizeof(d));
+    d.kind = v.kind;
+    d.n_map = v.n_map;
+    d.mass = v.mass;
+    d.mu_g = v.mu_g;
+    d.f_max = v.f_max;
+    d.f_max_sq = v.f_max_sq;
+    d.e0 = v.e0;
+    d.cr2 = v.cr2;
+    for (int i = 0; i < LTK_MAX_ENGINE_MAP; ++i) {
+        d.map_v[i] = v.map_v[i];
+        d.map_f[i] = v.map_f[i];
+    }
+    // slope of each engine-map segment exactly as np.interp forms it: (f[j+1]-f[j])/(v[j+1]-v[j])
+    for (int i = 0; i + 1 < v.n_map && i + 1 < LTK_MAX_ENGINE_MAP; ++i)
+        d.map_s[i] = (v.map_f[i + 1] - v.map_f[i]) / (v.map_v[i + 1] - v.map_v[i]);
+    return d;
+}
+
+int check_vehicle(const ltk_vehicle* v)
+{
+    if (!v) return 0;
+    if (v->kind != 0 && v->kind != 1) return 0;
+    if (v->kind == 0 && (v->n_map < 2 || v->n_map > LTK_MAX_ENGINE_MAP)) return 0;
+    if (!(v->mass > 0.0)) return 0;
+    return 1;
+}
+
+struct WsLayout {
+    long long Bp;
+    size_t kap_off, vacc_off, len_off, rot_off, vdec_off, vmin_off, total;
+};
+
+WsLayout ws_layout(int ns, long long B, bool dumps)
+{
+    WsLayout w;
+    w.Bp = round_up(B < 1 ? 1 : B, 32);
+    size_t rows = (size_t)(ns - 1);
+    size_t arr = rows * (size_t)w.Bp * sizeof(double);
+    size_t off = 0;
+    w.kap_off = off; off += arr;
+    w.vacc_off = off; off += arr;
+    w.len_off = off; off += (size_t)w.Bp * sizeof(double);
+    w.rot_off = off; off += round_up((long long)w.Bp * sizeof(int), 256);
+    w.vdec_off = w.vmin_off = 0;
+    if (dumps) {
+        w.vdec_off = off; off += arr;
+        w.vmin_off = off; off += arr;
+    }
+    w.total = off;
+    return w;
+}
+
+struct K1Config {
+    int G, staged;
+    size_t smem;
+};
+
+bool pick_k1(const ltk_ctx* ctx, K1Config* out)
+{
+    const int cand_g[2] = {16, 8};
+    for (int staged = 1; staged >= 0; --staged) {
+        if (ctx->k1_staged_override >= 0 && staged != ctx->k1_staged_override) continue;
+        for (int gi = 0; gi < 2; ++gi) {
+            int G = cand_g[gi];
+            if (ctx->k1_g_override > 0 && G != ctx->k1_g_override) continue;
+            size_t s = k1_smem_bytes(G, ctx->N, ctx->ns, staged);
+            if (s <= ctx->smem_optin) {
+                out->G = G; out->staged = staged; out->smem = s;
+                return true;
+            }
+        }
+    }
+    return false;
+}
+
+template <int G>
+cudaError_t launch_k1(const K1Args& a, size_t smem, cudaStream_t st)
+{
+    cudaError_t e = cudaFuncSetAttribute(k1_curvature<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    unsigned grid = (unsigned)(a.Bp / G);
+    k1_curvature<G><<<grid, K1_THREADS, smem, st>>>(a);
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
+}
+
+// the three pipeline launches on a laid-out workspace
+int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m, long long B,
+                 double* d_lap, char* ws, const WsLayout& w, bool dumps, cudaStream_t st)
+{
+    K1Config cfg;
+    if (!pick_k1(ctx, &cfg)) return fail(ctx, LTK_E_UNSUPPORTED, "control-point count too large for shared memory");
+    K1Args a;
+    a.alphas = d_alphas; a.xy = d_xy; a.mode = d_xy ? 1 : 0; a.m = m;
+    a.left = ctx->d_left; a.diff = ctx->d_diff; a.N = ctx->N; a.ns = ctx->ns;
+    a.B = B; a.Bp = w.Bp;
+    a.kap = reinterpret_cast<double*>(ws + w.kap_off);
+    a.rot = reinterpret_cast<int*>(ws + w.rot_off);
+    a.len = reinterpret_cast<double*>(ws + w.len_off);
+    a.staged = cfg.staged;
+    LTK_CUDA(ctx, cfg.G == 16 ? launch_k1<16>(a, cfg.smem, st) : launch_k1<8>(a, cfg.smem, st));
+
+    SweepArgs s;
+    s.kap = a.kap;
+    s.vacc = reinterpret_cast<double*>(ws + w.vacc_off);
+    s.rot = a.rot; s.len = a.len; s.lap = d_lap;
+    s.vdec = dumps ? reinterpret_cast<double*>(ws + w.vdec_off) : nullptr;
+    s.vmin = dumps ? reinterpret_cast<double*>(ws + w.vmin_off) : nullptr;
+    s.ns = ctx->ns; s.B = B; s.Bp = w.Bp;
+    unsigned grid = (unsigned)((B + SWEEP_THREADS - 1) / SWEEP_THREADS);
+    if (ctx->veh.kind == 0) {
+        k2_forward<0><<<grid, SWEEP_THREADS, 0, st>>>(s, ctx->veh);
+        k3_backward<0><<<grid, SWEEP_THREADS, 0, st>>>(s, ctx->veh);
+    } else {
+        k2_forward<1><<<grid, SWEEP_THREADS, 0, st>>>(s, ctx->veh);
+        k3_backward<1><<<grid, SWEEP_THREADS, 0, st>>>(s, ctx->veh);
+    }
+    g_launches.fetch_add(2);
+    LTK_CUDA(ctx, cudaGetLastError());
+    return LTK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ltk_version(void) { return 100; }
+int64_t ltk_launch_count(void) { return (int64_t)g_launches.load(); }
+
+const char* ltk_last_error(const ltk_ctx* ctx) { return ctx ? ctx->err : g_create_err; }
+
+int ltk_create(ltk_ctx** out, int device, const double* h_left_xy, const double* h_diff_xy, int n_ctrl,
+               const ltk_vehicle* vehicle, int ns)
+{
+    if (!out || !h_left_xy || !h_diff_xy) return fail(nullptr, LTK_E_ARG, "null argument");
+    if (n_ctrl < 3) return fail(nullptr, LTK_E_ARG, "need at least 3 unique control points");
+    if (ns < 3) return fail(nullptr, LTK_E_ARG, "ns must be >= 3");
+    if (!check_vehicle(vehicle)) return fail(nullptr, LTK_E_ARG, "bad vehicle description");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess) return fail(nullptr, LTK_E_CUDA, "cudaGetDeviceCount", e);
+    if (device < 0 || device >= ndev) return fail(nullptr, LTK_E_ARG, "no such CUDA device");
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return fail(nullptr, LTK_E_CUDA, "cudaGetDeviceProperties", e);
+    if (prop.major != 10) return fail(nullptr, LTK_E_UNSUPPORTED, "ltk kernels are built for sm_100a (B200) only");
+
+    ltk_ctx* ctx = new (std::nothrow) ltk_ctx;
+    if (!ctx) return fail(nullptr, LTK_E_ARG, "out of host memory");
+    memset(ctx, 0, sizeof(*ctx));
+    ctx->device = device;
+    ctx->N = n_ctrl;
+    ctx->ns = ns;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    ctx->veh = make_vehdev(*vehicle);
+    ctx->k1_g_override = 0;
+    ctx->k1_staged_override = -1;
+    if (const char* s = getenv("LTK_K1_G")) ctx->k1_g_override = atoi(s);
+    if (const char* s = getenv("LTK_K1_STAGED")) ctx->k1_staged_override = atoi(s);
+    size_t bytes = sizeof(double) * 2 * (size_t)n_ctrl;
+    if ((e = cudaMalloc(&ctx->d_left, bytes)) != cudaSuccess || (e = cudaMalloc(&ctx->d_diff, bytes)) != cudaSuccess ||
+        (e = cudaMalloc(&ctx->d_topk_lap, sizeof(double) * TOPK_MAX_BLOCKS * TOPK_MAX)) != cudaSuccess ||
+        (e = cudaMalloc(&ctx->d_topk_idx, sizeof(long long) * TOPK_MAX_BLOCKS * TOPK_MAX)) != cudaSuccess ||
+        (e = cudaMemcpy(ctx->d_left, h_left_xy, bytes, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(ctx->d_diff, h_diff_xy, bytes, cudaMemcpyHostToDevice)) != cudaSuccess) {
+        fail(nullptr, LTK_E_CUDA, "context allocation", e);
+        ltk_destroy(ctx);
+        return LTK_E_CUDA;
+    }
+    K1Config cfg;
+    if (!pick_k1(ctx, &cfg)) {
+        fail(nullptr, LTK_E_UNSUPPORTED, "control-point count too large for shared memory");
+        ltk_destroy(ctx);
+        return LTK_E_UNSUPPORTED;
+    }
+    *out = ctx;
+    return LTK_OK;
+}
+
+void ltk_destroy(ltk_ctx* ctx)
+{
+    if (!ctx) return;
+    DeviceGuard guard(ctx->device);
+    cudaFree(ctx->d_left);
+    cudaFree(ctx->d_diff);
+    cudaFree(ctx->d_topk_lap);
+    cudaFree(ctx->d_topk_idx);
+    cudaFree(ctx->d_profile_ws);
+    delete ctx;
+}
+
+int ltk_set_ns(ltk_ctx* ctx, int ns)
+{
+    if (!ctx) return LTK_E_ARG;
+    if (ns < 3) return fail(ctx, LTK_E_ARG, "ns must be >= 3");
+    int old = ctx->ns;
+    ctx->ns = ns;
+    K1Config cfg;
+    if (!pick_k1(ctx, &cfg)) {
+        ctx->ns = old;
+        return fail(ctx, LTK_E_UNSUPPORTED, "no K1 configuration fits shared memory");
+    }
+    return LTK_OK;
+}
+
+int ltk_workspace_bytes(const ltk_ctx* ctx, int64_t B, size_t* out_bytes)
+{
+    if (!ctx || !out_bytes || B < 0) return LTK_E_ARG;
+    *out_bytes = ws_layout(ctx->ns, B, false).total;
+    return LTK_OK;
+}
+
+int ltk_eval_alphas(ltk_ctx* ctx, const double* d_alphas, int64_t B, double* d_lap, void* d_workspace,
+                    size_t workspace_bytes, void* stream)
+{
+    if (!ctx) return LTK_E_ARG;
+    if (B == 0) return LTK_OK;
+    if (!d_alphas || !d_lap || !d_workspace || B < 0) return fail(ctx, LTK_E_ARG, "null or negative argument");
+    WsLayout w = ws_layout(ctx->ns, B, false);
+    if (workspace_bytes < w.total) return fail(ctx, LTK_E_WORKSPACE, "workspace too small (see ltk_workspace_bytes)");
+    DeviceGuard guard(ctx->device);
+    return run_pipeline(ctx, d_alphas, nullptr, 0, B, d_lap, static_cast<char*>(d_workspace), w, false,
+                        static_cast<cudaStream_t>(stream));
+}
+
+int ltk_eval_controls(ltk_ctx* ctx, const double* d_xy, int m, int64_t B, double* d_lap, void* d_workspace,
+                      size_t workspace_bytes, void* stream)
+{
+    if (!ctx) return LTK_E_ARG;
+    if (B == 0) return LTK_OK;
+    if (!d_xy || !d_lap || !d_workspace || B < 0) return fail(ctx, LTK_E_ARG, "null or negative argument");
+    if (m != ctx->N + 1) return fail(ctx, LTK_E_ARG, "controls must have n_ctrl + 1 columns");
+    WsLayout w = ws_layout(ctx->ns, B, false);
+    if (workspace_bytes < w.total) return fail(ctx, LTK_E_WORKSPACE, "workspace too small (see ltk_workspace_bytes)");
+    DeviceGuard guard(ctx->device);
+    return run_pipeline(ctx, nullptr, d_xy, m, B, d_lap, static_cast<char*>(d_workspace), w, false,
+                        static_cast<cudaStream_t>(stream));
+}
+
+int ltk_profile(ltk_ctx* ctx, const double* d_alpha, double* d_s, double* d_k, double* d_vlocal, double* d_vacc,
+                double* d_vdec, double* d_v, double* d_scalars, void* stream)
+{
+    if (!ctx) return LTK_E_ARG;
+    if (!d_alpha) return fail(ctx, LTK_E_ARG, "null alpha");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    WsLayout w = ws_layout(ctx->ns, 1, true);
+    size_t need = w.total + 256;
+    if (ctx->profile_ws_bytes < need) {
+        LTK_CUDA(ctx, cudaStreamSynchronize(st));
+        cudaFree(ctx->d_profile_ws);
+        ctx->d_profile_ws = nullptr;
+        ctx->profile_ws_bytes = 0;
+        LTK_CUDA(ctx, cudaMalloc(&ctx->d_profile_ws, need));
+        ctx->profile_ws_bytes = need;
+    }
+    char* ws = static_cast<char*>(ctx->d_profile_ws);
+    double* d_lap = reinterpret_cast<double*>(ws + w.total);
+    int rc = run_pipeline(ctx, d_alpha, nullptr, 0, 1, d_lap, ws, w, true, st);
+    if (rc != LTK_OK) return rc;
+    unrotate_profile<<<8, 256, 0, st>>>(reinterpret_cast<double*>(ws + w.kap_off), reinterpret_cast<double*>(ws + w.vacc_off),
+                                        reinterpret_cast<double*>(ws + w.vdec_off), reinterpret_cast<double*>(ws + w.vmin_off),
+                                        reinterpret_cast<int*>(ws + w.rot_off), reinterpret_cast<double*>(ws + w.len_off),
+                                        ctx->ns, w.Bp, ctx->veh.mu_g, d_s, d_k, d_vlocal, d_vacc, d_vdec, d_v);
+    g_launches.fetch_add(1);
+    LTK_CUDA(ctx, cudaGetLastError());
+    if (d_scalars) {
+        LTK_CUDA(ctx, cudaMemcpyAsync(d_scalars, d_lap, sizeof(double), cudaMemcpyDeviceToDevice, st));
+        LTK_CUDA(ctx, cudaMemcpyAsync(d_scalars + 1, ws + w.len_off, sizeof(double), cudaMemcpyDeviceToDevice, st));
+    }
+    LTK_CUDA(ctx, cudaStreamSynchronize(st));
+    return LTK_OK;
+}
+
+int ltk_topk(ltk_ctx* ctx, const double* d_lap, int64_t B, int64_t index_base, int k, double* d_best_lap,
+             int64_t* d_best_idx, void* stream)
+{
+    if (!ctx) return LTK_E_ARG;
+    if (!d_lap || !d_best_lap || !d_best_idx || B < 0) return fail(ctx, LTK_E_ARG, "null or negative argument");
+    if (k < 1 || k > TOPK_MAX) return fail(ctx, LTK_E_ARG, "k must be in 1..64");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    long long nblk = (B + 8191) / 8192;
+    if (nblk < 1) nblk = 1;
+    if (nblk > TOPK_MAX_BLOCKS) nblk = TOPK_MAX_BLOCKS;
+    long long chunk = (B + nblk - 1) / nblk;
+    if (chunk < 1) chunk = 1;
+    long long* out_idx = reinterpret_cast<long long*>(d_best_idx);
+    if (nblk == 1) {
+        topk_select<<<1, TOPK_THREADS, 0, st>>>(d_lap, nullptr, B, chunk, index_base, k, d_best_lap, out_idx);
+        g_launches.fetch_add(1);
+    } else {
+        topk_select<<<(unsigned)nblk, TOPK_THREADS, 0, st>>>(d_lap, nullptr, B, chunk, index_base, k, ctx->d_topk_lap,
+                                                             ctx->d_topk_idx);
+        topk_select<<<1, TOPK_THREADS, 0, st>>>(ctx->d_topk_lap, ctx->d_topk_idx, nblk * k, nblk * k, 0, k, d_best_lap,
+                                                out_idx);
+        g_launches.fetch_add(2);
+    }
+    LTK_CUDA(ctx, cudaGetLastError());
+    return LTK_OK;
+}
+
+int ltk_path_eval(int device, const double* d_xy, const double* d_knots, int m, const double* d_u, int64_t n,
+                  double* d_x, double* d_y, double* d_dx, double* d_dy, double* d_ddx, double* d_ddy,
+                  double* d_k_signed, double* d_gamma2, void* stream)
+{
+    if (!d_xy || !d_knots || (!d_u && n > 0) || n < 0) return fail(nullptr, LTK_E_ARG, "null or negative argument");
+    if (m < 4) return fail(nullptr, LTK_E_ARG, "a closed path needs at least 3 unique points");
+    DeviceGuard guard(device);
+    int N = m - 1;
+    size_t smem = sizeof(double) * (size_t)(11 * N + N + 1);
+    cudaError_t e = cudaFuncSetAttribute(path_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(nullptr, LTK_E_UNSUPPORTED, "path too long for shared memory", e);
+    PathArgs a{d_xy, d_knots, m, d_u, n, d_x, d_y, d_dx, d_dy, d_ddx, d_ddy, d_k_signed, d_gamma2};
+    path_eval_kernel<<<1, 256, smem, static_cast<cudaStream_t>(stream)>>>(a);
+    g_launches.fetch_add(1);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(nullptr, LTK_E_CUDA, "path_eval_kernel", e);
+    return LTK_OK;
+}
+
+int ltk_velocity_profile(int device, const ltk_vehicle* vehicle, const double* d_s, const double* d_k, int64_t n,
+                         double s_max, double* d_vlocal, double* d_vacc, double* d_vdec, double* d_v, void* stream)
+{
+    if (!check_vehicle(vehicle)) return fail(nullptr, LTK_E_ARG, "bad vehicle description");
+    if (!d_s || !d_k || n < 1) return fail(nullptr, LTK_E_ARG, "null or empty samples");
+    if (!d_vacc || !d_vdec) return fail(nullptr, LTK_E_ARG, "d_vacc and d_vdec are required (they are the sweep state)");
+    DeviceGuard guard(device);
+    VehDev V = make_vehdev(*vehicle);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (V.kind == 0) velocity_profile_kernel<0><<<1, 32, 0, st>>>(V, d_s, d_k, n, s_max, d_vlocal, d_vacc, d_vdec, d_v);
+    else velocity_profile_kernel<1><<<1, 32, 0, st>>>(V, d_s, d_k, n, s_max, d_vlocal, d_vacc, d_vdec, d_v);
+    g_launches.fetch_add(1);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(nullptr, LTK_E_CUDA, "velocity_profile_kernel", e);
+    return LTK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,173 @@
+"""`LapTimeEvaluator` -- the batched entry point: alphas[B, N_alpha] -> lap[B] on one B200.
+
+Owns one `ltk_ctx` (track constants, vehicle constants, sampling), a reusable device workspace and a
+pinned host staging buffer.  Inputs may be torch CUDA tensors (stay resident) or host arrays (copied
+through pinned memory).  Everything numeric happens in libltk's kernels."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _device, _native
+
+DEFAULT_TOPK = 10  # trajectory_bayesian_nonlinear.py:257
+
+
+class LapTimeEvaluator:
+    def __init__(self, track, vehicle, mode="bayes", ns=None, device=None, max_workspace_bytes=None):
+        torch = _device.torch_cuda()
+        self.torch = torch
+        self.lib = _native.load()
+        self.track, self.vehicle, self.mode = track, vehicle, mode
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
+        self.ns = int(math.ceil(track.length) if ns is None else ns)  # trajectory.py:35
+        left, diff = track.affine_map(mode)
+        self.n_alpha = left.shape[1]
+        self._veh = vehicle.to_ltk()
+        handle = C.c_void_p()
+        dp = C.POINTER(C.c_double)
+        rc = self.lib.ltk_create(C.byref(handle), self.device.index, left.ctypes.data_as(dp),
+                                 diff.ctypes.data_as(dp), self.n_alpha, C.byref(self._veh), self.ns)
+        _native.check(rc)
+        self._ctx = handle
+        self._ws = None
+        self._pinned = None
+        self._pinned_out = None
+        if max_workspace_bytes is None:
+            free, _total = torch.cuda.mem_get_info(self.device)
+            max_workspace_bytes = int(free * 0.8)
+        self.max_workspace_bytes = max_workspace_bytes
+
+    # -- lifetime ---------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self.lib.ltk_destroy(self._ctx)
+            self._ctx = None
+        self._ws = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_ns(self, ns):
+        """`Trajectory.ns` is a plain attribute in the reference; changing it re-samples the lap."""
+        _native.check(self.lib.ltk_set_ns(self._ctx, int(ns)), self._ctx)
+        self.ns = int(ns)
+
+    # -- sizing -----------------------------------------------------------------------------------
+    def workspace_bytes(self, B):
+        out = C.c_size_t()
+        _native.check(self.lib.ltk_workspace_bytes(self._ctx, int(B), C.byref(out)), self._ctx)
+        return out.value
+
+    def max_batch(self):
+        """Largest candidate count whose workspace fits the budget (multiple of 4096)."""
+        per = self.workspace_bytes(4096) / 4096.0
+        b = int(self.max_workspace_bytes / per) // 4096 * 4096
+        return max(b, 32)
+
+    def _workspace(self, B):
+        need = self.workspace_bytes(B)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = self.torch.empty(need, dtype=self.torch.uint8, device=self.device)
+        return self._ws
+
+    # -- evaluation -------------------------------------------------------------------------------
+    def lap_times_device(self, alphas, out=None):
+        """alphas: float64 CUDA tensor [B, n_alpha] (contiguous) -> float64 CUDA tensor [B].
+        Asynchronous on the current stream."""
+        torch = self.torch
+        if alphas.dtype != torch.float64 or not alphas.is_cuda or not alphas.is_contiguous():
+            raise ValueError("alphas must be a contiguous float64 CUDA tensor")
+        if alphas.dim() != 2 or alphas.shape[1] != self.n_alpha:
+            raise ValueError(f"alphas must be [B, {self.n_alpha}]")
+        B = alphas.shape[0]
+        if out is None:
+            out = torch.empty(B, dtype=torch.float64, device=self.device)
+        chunk = self.max_batch()
+        st = _device.stream_ptr(torch, self.device)
+        for lo in range(0, B, chunk):
+            hi = min(B, lo + chunk)
+            ws = self._workspace(hi - lo)
+            rc = self.lib.ltk_eval_alphas(self._ctx, _device.ptr(alphas[lo:hi]), hi - lo, _device.ptr(out[lo:hi]),
+                                          _device.ptr(ws), ws.numel(), st)
+            _native.check(rc, self._ctx)
+        return out
+
+    def controls_lap_times_device(self, xy, out=None):
+        """xy: float64 CUDA tensor [B, 2, n_alpha + 1] of control points (calcMinTime surface)."""
+        torch = self.torch
+        if xy.dtype != torch.float64 or not xy.is_cuda or not xy.is_contiguous():
+            raise ValueError("controls must be a contiguous float64 CUDA tensor")
+        if xy.dim() != 3 or xy.shape[1] != 2 or xy.shape[2] != self.n_alpha + 1:
+            raise ValueError(f"controls must be [B, 2, {self.n_alpha + 1}]")
+        B = xy.shape[0]
+        if out is None:
+            out = torch.empty(B, dtype=torch.float64, device=self.device)
+        chunk = self.max_batch()
+        st = _device.stream_ptr(torch, self.device)
+        for lo in range(0, B, chunk):
+            hi = min(B, lo + chunk)
+            ws = self._workspace(hi - lo)
+            rc = self.lib.ltk_eval_controls(self._ctx, _device.ptr(xy[lo:hi]), xy.shape[2], hi - lo,
+                                            _device.ptr(out[lo:hi]), _device.ptr(ws), ws.numel(), st)
+            _native.check(rc, self._ctx)
+        return out
+
+    def lap_times(self, alphas):
+        """Host in, host out: numpy [B, n_alpha] -> numpy [B], through pinned staging buffers."""
+        torch = self.torch
+        a = np.ascontiguousarray(alphas, dtype=np.float64)
+        if a.ndim == 1:
+            a = a.reshape(1, -1)
+        B = a.shape[0]
+        if self._pinned is None or self._pinned.shape[0] < B:
+            self._pinned = torch.empty((B, self.n_alpha), dtype=torch.float64).pin_memory()
+            self._pinned_out = torch.empty(B, dtype=torch.float64).pin_memory()
+        self._pinned[:B].copy_(torch.from_numpy(a))
+        d_a = self._pinned[:B].to(self.device, non_blocking=True)
+        d_lap = self.lap_times_device(d_a)
+        self._pinned_out[:B].copy_(d_lap, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self._pinned_out[:B].numpy().copy()
+
+    def topk_device(self, laps, k=DEFAULT_TOPK, index_base=0):
+        """Stable ascending top-k of a CUDA lap tensor -> (lap[k], idx[k]) CUDA tensors."""
+        torch = self.torch
+        best = torch.empty(k, dtype=torch.float64, device=self.device)
+        idx = torch.empty(k, dtype=torch.int64, device=self.device)
+        rc = self.lib.ltk_topk(self._ctx, _device.ptr(laps), laps.numel(), int(index_base), int(k),
+                               _device.ptr(best), _device.ptr(idx), _device.stream_ptr(torch, self.device))
+        _native.check(rc, self._ctx)
+        return best, idx
+
+    def topk(self, laps, k=DEFAULT_TOPK, index_base=0):
+        if isinstance(laps, np.ndarray):
+            laps = _device.to_device(laps, self.device)
+        best, idx = self.topk_device(laps, k, index_base)
+        return best.cpu().numpy(), idx.cpu().numpy()
+
+    def profile(self, alpha):
+        """Everything the reference exposes for ONE candidate (natural sample order), as numpy."""
+        torch = self.torch
+        a = _device.to_device(np.asarray(alpha, dtype=np.float64).reshape(-1), self.device)
+        if a.numel() != self.n_alpha:
+            raise ValueError(f"alpha must have {self.n_alpha} entries")
+        n = self.ns - 1
+        names = ("k", "v_local", "v_acclim", "v_declim", "v")
+        d_s = torch.empty(self.ns, dtype=torch.float64, device=self.device)
+        bufs = {nm: torch.empty(n, dtype=torch.float64, device=self.device) for nm in names}
+        scal = torch.empty(2, dtype=torch.float64, device=self.device)
+        rc = self.lib.ltk_profile(self._ctx, _device.ptr(a), _device.ptr(d_s), *[_device.ptr(bufs[nm]) for nm in names],
+                                  _device.ptr(scal), _device.stream_ptr(torch, self.device))
+        _native.check(rc, self._ctx)
+        out = {nm: b.cpu().numpy() for nm, b in bufs.items()}
+        out["s"] = d_s.cpu().numpy()
+        sc = scal.cpu().numpy()
+        out["lap"], out["length"] = np.float64(sc[0]), np.float64(sc[1])
+        return out

@@ -1,0 +1,109 @@
+"""`TrajectoryBayesianNonlinear` facade (reference src/trajectory_bayesian_nonlinear.py:22-80, :230-257).
+
+Keeps `update`, `lap_time`, `updateAlphas`, `calcMinTime` and adds the batched population stage the
+reference runs one candidate at a time (`Nonlinear`, :239-257; `Bayesian` database, :136-160):
+`lap_time_batch`, `random_population`, `population_topk`."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from . import _device
+from .evaluator import DEFAULT_TOPK, LapTimeEvaluator
+from .path import Path
+from .velocity import VelocityProfile
+
+ALPHA_LOW, ALPHA_HIGH = 0.0, 0.99  # trajectory_bayesian_nonlinear.py:142, :244
+
+
+class TrajectoryBayesianNonlinear:
+    MODE = "bayes"
+
+    def __init__(self, track, vehicle, device=None):
+        self.track = track
+        self.ns = math.ceil(track.length)
+        self.vehicle = vehicle
+        self._device = device
+        self._evaluator = None
+        self._velocity = None
+        self._lap = None
+        self.update(np.full(track.size, 0.5))
+        self.direction_vector = track.diffs
+        self.length = track.length
+        self.mid_waipoints = track.mid_controls
+        self.mid_controls_decongested = track.mid_controls_decongested
+        self.widths_decongested = track.widths_decongested
+        self.best = []
+        self.sigma = []
+
+    @property
+    def evaluator(self) -> LapTimeEvaluator:
+        if self._evaluator is None:
+            self._evaluator = LapTimeEvaluator(self.track, self.vehicle, self.MODE, self.ns, self._device)
+        elif self._evaluator.ns != self.ns:
+            self._evaluator.set_ns(self.ns)
+        return self._evaluator
+
+    @property
+    def n_alpha(self):
+        return self.track.left_decongested.shape[1] - 1
+
+    # -- reference surface ------------------------------------------------------------------------
+    def update(self, alphas):
+        """Full-resolution control points and path (tbn.py:44-49)."""
+        self.alphas = alphas
+        self.path = Path(self.track.control_points(alphas), self.track.closed)
+        self.s = np.linspace(0, self.path.length, self.ns)
+
+    @property
+    def velocity(self):
+        """Velocity profile of the last `calcMinTime` path, materialised on first access."""
+        if self._velocity is None and self._lap is not None:
+            s = self.s[:-1]
+            s_max = self.path.length if self.track.closed else None
+            self._velocity = VelocityProfile(self.vehicle, s, self.path.curvature(s), s_max)
+        return self._velocity
+
+    @velocity.setter
+    def velocity(self, value):
+        self._velocity = value
+
+    def lap_time(self):
+        """Lap time of the last evaluated path (tbn.py:51-54)."""
+        return self._lap
+
+    def updateAlphas(self, alphas):
+        """alphas on the every-3rd-cone subset -> closed control polygon [2, m] (tbn.py:58-62)."""
+        return Path(self.track.control_points_bayesian(alphas), self.track.closed).controls
+
+    def calcMinTime(self, controls):
+        """Minimum lap time along the spline through `controls` (tbn.py:65-80)."""
+        controls = np.asarray(controls, dtype=np.float64)
+        self.path = Path(controls, self.track.closed)
+        self.s = np.linspace(0, self.path.length, self.ns)
+        self._velocity = None
+        ev = self.evaluator
+        xy = _device.to_device(controls.reshape(1, 2, -1), ev.device)
+        self._lap = np.float64(ev.controls_lap_times_device(xy).cpu().numpy()[0])
+        return self._lap
+
+    # -- batched surface --------------------------------------------------------------------------
+    def lap_time_batch(self, alphas):
+        """alphas [B, n_alpha] (numpy or CUDA tensor) -> lap times [B] of the same kind."""
+        if isinstance(alphas, np.ndarray) or not hasattr(alphas, "is_cuda"):
+            return self.evaluator.lap_times(alphas)
+        return self.evaluator.lap_times_device(alphas)
+
+    def random_population(self, count, seed=None):
+        """`count` candidates with every alpha ~ U[0, 0.99) (tbn.py:142, :244)."""
+        return np.random.default_rng(seed).uniform(ALPHA_LOW, ALPHA_HIGH, (count, self.n_alpha))
+
+    def population_topk(self, alphas, k=DEFAULT_TOPK):
+        """Score a population and keep the k fastest: what `sorted(results)[0:10]` feeds to COBYLA
+        (tbn.py:253-257).  Returns (laps[B], best_laps[k], best_indices[k]) as numpy arrays."""
+        ev = self.evaluator
+        d_a = alphas if hasattr(alphas, "is_cuda") else _device.to_device(alphas, ev.device)
+        d_lap = ev.lap_times_device(d_a)
+        best, idx = ev.topk_device(d_lap, k)
+        return d_lap.cpu().numpy(), best.cpu().numpy(), idx.cpu().numpy()
