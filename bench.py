@@ -1,0 +1,316 @@
+#!/usr/bin/env python3
+"""bench.py -- lap-time evaluations/sec on Buckmore + TBR18 (BASELINE.json), B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" scores one population of `--candidates` (default 65,536 = BASELINE.json configs[1]) random
+alpha vectors per GPU: K1 spline+curvature -> K2 forward sweep -> K3 backward sweep + lap sum ->
+top-10 (-> one all-gather of 160 B/rank + merge when N > 1).  Candidates are independent, so ranks
+get disjoint populations and the scaling is weak.  Prints ONE JSON line (rank 0).
+
+`value`   : whole-job evaluations/s, inputs already resident in HBM, CUDA-event timed, max over ranks.
+`e2e`     : same metric through the public host API (numpy in pinned memory -> H2D -> pipeline -> top-k
+            -> D2H of all lap times and the top-10) at N GPUs.
+`roofline`: the dominant kernel's algorithmic bytes / its CUDA-event duration against the measured HBM
+            peak (MEASURED_PEAKS.json, burst figure; fallback 6650 GB/s per B200_PROFILING.md).
+`cpu_baseline` / `--impl reference`: the reference's own CPU path (oracle/reference_port.py: the
+            reference restated one candidate at a time with the same SciPy/numpy calls, pinned
+            bit-for-bit to the unmodified reference by tests/golden) on all host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TRACK, VEHICLE, WIDTH = "buckmore", "tbr18", 0.8
+TOPK = 10
+METRIC = "lap_time_evals_per_sec"
+UNIT = "evals/s"
+N_INPUT_SETS = 8  # distinct resident populations cycled through the steps (8 x 22.5 MB > 126 MB L2)
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--candidates", type=int, default=65536, help="candidates per GPU per step")
+    p.add_argument("--vehicle", default=VEHICLE, choices=["tbr18", "MX5"])
+    p.add_argument("--ns", type=int, default=None, help="samples per lap incl. end point (default ceil(track length) = 847)")
+    p.add_argument("--cpu-sample", type=int, default=2048, help="candidates scored by the CPU baseline")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    return p.parse_args()
+
+
+def data_paths(vehicle):
+    import lap_time_optimization_b200 as ltk
+
+    return ltk.data_path("tracks", TRACK + ".json"), ltk.data_path("vehicles", vehicle + ".json")
+
+
+def workload_config(args, n_alpha, ns):
+    return {"workload": f"{TRACK} track + {args.vehicle} vehicle, width {WIDTH}, random alpha ~ U[0,0.99)^{n_alpha}, "
+                        f"{args.candidates} candidates per GPU per step, {ns - 1} samples per lap, top-{TOPK}",
+            "candidates_per_gpu": args.candidates, "n_alpha": n_alpha, "samples_per_lap": ns - 1, "topk": TOPK,
+            "l2": f"{N_INPUT_SETS} distinct resident populations cycled (inputs {N_INPUT_SETS}x{args.candidates * n_alpha * 8 / 1e6:.1f} MB) and "
+                  f"{2 * (ns - 1) * args.candidates * 8 / 1e9:.2f} GB of staged intermediates rewritten every step (> 126 MB L2)"}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm
+# ------------------------------------------------------------------------------------------------
+def cpu_rate(args, sample, processes):
+    """evals/s of the reference-equivalent CPU port on `processes` host processes."""
+    from oracle.reference_port import lap_times_pool
+
+    tj, vj = data_paths(args.vehicle)
+    n_alpha = 43
+    a = np.random.default_rng(1002).uniform(0.0, 0.99, (sample, n_alpha))
+    t0 = time.perf_counter()
+    laps = lap_times_pool(tj, WIDTH, vj, a, "bayes", args.ns, processes)
+    dt = time.perf_counter() - t0
+    return sample / dt, laps, a
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = max(64, min(args.cpu_sample, 64 * cores) // 4)  # per step; bounded so K+W steps stay within minutes
+    rates = []
+    for i in range(args.warmup + args.steps):
+        r, _, _ = cpu_rate(args, sample, cores)
+        if i >= args.warmup:
+            rates.append(r)
+    value = float(np.mean(rates))
+    ns = args.ns or 847
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sample / value,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, 43, ns),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{sample} candidates per step, fork pool of {cores} processes, "
+                                       "oracle/reference_port.py (reference restated with the same SciPy FITPACK / numpy calls)"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append((time.perf_counter(), ln.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        picked = [r for (t, r) in self.rows if t0 <= t <= t1] or [r for (_, r) in self.rows[-3:]]
+        for r in picked:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except Exception:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(picked)}
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import lap_time_optimization_b200 as ltk
+    from lap_time_optimization_b200 import _native
+    from lap_time_optimization_b200.distributed import allgather_topk
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    tj, vj = data_paths(args.vehicle)
+    track = ltk.Track(tj, track_width=WIDTH, quiet=True)
+    ev = ltk.LapTimeEvaluator(track, ltk.load_vehicle(vj), "bayes", args.ns, device=local)
+    B, na, ns = args.candidates, ev.n_alpha, ev.ns
+    base = rank * B  # global index of this rank's first candidate
+    # resident inputs: N_INPUT_SETS distinct populations per rank
+    host_sets = [np.random.default_rng(1002 + 7919 * rank + i).uniform(0.0, 0.99, (B, na)) for i in range(N_INPUT_SETS)]
+    dev_sets = [torch.as_tensor(h).to(dev) for h in host_sets]
+    d_lap = torch.empty(B, dtype=torch.float64, device=dev)
+
+    def step(i):
+        ev.lap_times_device(dev_sets[i % N_INPUT_SETS], out=d_lap)
+        best, idx = ev.topk_device(d_lap, TOPK, index_base=base)
+        if world > 1:
+            best, idx = allgather_topk(best, idx, TOPK, merge=ev.merge_topk_device)
+        return best, idx
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.15)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = _native.launch_count()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(args.steps):
+        best, idx = step(i)
+    e1.record()
+    barrier()
+    t1 = time.perf_counter()
+    launches = _native.launch_count() - l0
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    value = world * B * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end: host numpy -> pinned -> H2D -> pipeline -> top-k -> D2H ---------------------
+    pin_in = [torch.as_tensor(h).pin_memory() for h in host_sets[:2]]
+    pin_lap = torch.empty(B, dtype=torch.float64).pin_memory()
+    pin_best = torch.empty(TOPK, dtype=torch.float64).pin_memory()
+    pin_idx = torch.empty(TOPK, dtype=torch.int64).pin_memory()
+    d_in = torch.empty((B, na), dtype=torch.float64, device=dev)
+
+    def e2e_step(i):
+        d_in.copy_(pin_in[i % 2], non_blocking=True)
+        ev.lap_times_device(d_in, out=d_lap)
+        b, ix = ev.topk_device(d_lap, TOPK, index_base=base)
+        if world > 1:
+            b, ix = allgather_topk(b, ix, TOPK, merge=ev.merge_topk_device)
+        pin_lap.copy_(d_lap, non_blocking=True)
+        pin_best.copy_(b, non_blocking=True)
+        pin_idx.copy_(ix, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    t0e = time.perf_counter()
+    for i in range(args.steps):
+        e2e_step(i)
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / float(dt.item())
+
+    # ---- per-kernel durations (CUDA events on the launching stream), same workload ---------------
+    kt = ev.kernel_times(dev_sets[0], d_lap, reps=max(3, min(args.steps, 10)))
+
+    if rank == 0:
+        n = ns - 1
+        peak, peak_src = hbm_peak()
+        alg = {"k1_curvature": 8 * na + 8 * n, "k2_forward": 16 * n, "k3_backward": 16 * n + 8}
+        dom = max(kt, key=lambda k: kt[k])
+        achieved = alg[dom] * B / (kt[dom] * 1e-3) / 1e9
+        a_staged = sum(alg.values())
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(dom)
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, na, ns),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * na * 8,
+                    "d2h_bytes_per_step": B * 8 + TOPK * 16},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_candidate": alg[dom],
+                         "kernel_ms": {k: round(v, 4) for k, v in kt.items()},
+                         "pipeline": {"bytes_per_candidate": a_staged,
+                                      "achieved": a_staged * B * world / (ms_total / args.steps * 1e-3) / 1e9 / world,
+                                      "frac": a_staged * B / (ms_total / args.steps * 1e-3) / 1e9 / peak}},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            rate, cpu_laps, cpu_a = cpu_rate(args, args.cpu_sample, cores)
+            gpu_laps = ev.lap_times(cpu_a)
+            rel = np.abs(gpu_laps - cpu_laps) / cpu_laps
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{args.cpu_sample} candidates of the same distribution, fork pool of {cores} "
+                                              "processes, oracle/reference_port.py",
+                                    "parity_rel_err": {"median": float(np.median(rel)), "p99": float(np.percentile(rel, 99)),
+                                                       "max": float(rel.max())}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

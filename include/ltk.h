@@ -82,6 +82,11 @@ int ltk_workspace_bytes(const ltk_ctx *ctx, int64_t B, size_t *out_bytes);
 int ltk_eval_alphas(ltk_ctx *ctx, const double *d_alphas, int64_t B, double *d_lap,
                     void *d_workspace, size_t workspace_bytes, void *stream);
 
+/* Measurement hook: same work as ltk_eval_alphas, with CUDA events recorded on `stream` around each of
+ * the three kernels; synchronises and writes their durations in milliseconds to h_ms[3] = {K1, K2, K3}. */
+int ltk_eval_alphas_timed(ltk_ctx *ctx, const double *d_alphas, int64_t B, double *d_lap,
+                          void *d_workspace, size_t workspace_bytes, void *stream, float *h_ms);
+
 /* control points -> lap times: the calcMinTime(controls) surface
  * (trajectory_bayesian_nonlinear.py:65-80).  d_xy [B][2][m] row-major with m = n_ctrl + 1 columns
  * (the last column is the closing duplicate and is ignored, exactly as splprep(per=1) overwrites it). */
@@ -114,6 +119,11 @@ int ltk_path_eval(int device, const double *d_xy, const double *d_knots, int m, 
 int ltk_velocity_profile(int device, const ltk_vehicle *vehicle, const double *d_s, const double *d_k,
                          int64_t n, double s_max, double *d_vlocal, double *d_vacc, double *d_vdec,
                          double *d_v, void *stream);
+
+/* Merge step of the multi-GPU top-k: stable ascending top-k of explicit (lap, index) pairs, e.g. the
+ * all-gathered per-rank winners. Entries with index < 0 are padding. */
+int ltk_topk_pairs(ltk_ctx *ctx, const double *d_lap, const int64_t *d_idx, int64_t count, int k,
+                   double *d_best_lap, int64_t *d_best_idx, void *stream);
 
 /* Library/ABI version and a count of kernel launches issued through this library since load
  * (bench.py reports it as gpu_launches). */

@@ -155,7 +155,8 @@ cudaError_t launch_k1(const K1Args& a, size_t smem, cudaStream_t st)
 
 // the three pipeline launches on a laid-out workspace
 int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m, long long B,
-                 double* d_lap, char* ws, const WsLayout& w, bool dumps, cudaStream_t st)
+                 double* d_lap, char* ws, const WsLayout& w, bool dumps, cudaStream_t st,
+                 cudaEvent_t* ev = nullptr)
 {
     K1Config cfg;
     if (!pick_k1(ctx, &cfg)) return fail(ctx, LTK_E_UNSUPPORTED, "control-point count too large for shared memory");
@@ -167,7 +168,9 @@ int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m
     a.rot = reinterpret_cast<int*>(ws + w.rot_off);
     a.len = reinterpret_cast<double*>(ws + w.len_off);
     a.staged = cfg.staged;
+    if (ev) LTK_CUDA(ctx, cudaEventRecord(ev[0], st));
     LTK_CUDA(ctx, cfg.G == 16 ? launch_k1<16>(a, cfg.smem, st) : launch_k1<8>(a, cfg.smem, st));
+    if (ev) LTK_CUDA(ctx, cudaEventRecord(ev[1], st));
 
     SweepArgs s;
     s.kap = a.kap;
@@ -177,13 +180,12 @@ int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m
     s.vmin = dumps ? reinterpret_cast<double*>(ws + w.vmin_off) : nullptr;
     s.ns = ctx->ns; s.B = B; s.Bp = w.Bp;
     unsigned grid = (unsigned)((B + SWEEP_THREADS - 1) / SWEEP_THREADS);
-    if (ctx->veh.kind == 0) {
-        k2_forward<0><<<grid, SWEEP_THREADS, 0, st>>>(s, ctx->veh);
-        k3_backward<0><<<grid, SWEEP_THREADS, 0, st>>>(s, ctx->veh);
-    } else {
-        k2_forward<1><<<grid, SWEEP_THREADS, 0, st>>>(s, ctx->veh);
-        k3_backward<1><<<grid, SWEEP_THREADS, 0, st>>>(s, ctx->veh);
-    }
+    if (ctx->veh.kind == 0) k2_forward<0><<<grid, SWEEP_THREADS, 0, st>>>(s, ctx->veh);
+    else k2_forward<1><<<grid, SWEEP_THREADS, 0, st>>>(s, ctx->veh);
+    if (ev) LTK_CUDA(ctx, cudaEventRecord(ev[2], st));
+    if (ctx->veh.kind == 0) k3_backward<0><<<grid, SWEEP_THREADS, 0, st>>>(s, ctx->veh);
+    else k3_backward<1><<<grid, SWEEP_THREADS, 0, st>>>(s, ctx->veh);
+    if (ev) LTK_CUDA(ctx, cudaEventRecord(ev[3], st));
     g_launches.fetch_add(2);
     LTK_CUDA(ctx, cudaGetLastError());
     return LTK_OK;
@@ -292,6 +294,42 @@ int ltk_eval_alphas(ltk_ctx* ctx, const double* d_alphas, int64_t B, double* d_l
     DeviceGuard guard(ctx->device);
     return run_pipeline(ctx, d_alphas, nullptr, 0, B, d_lap, static_cast<char*>(d_workspace), w, false,
                         static_cast<cudaStream_t>(stream));
+}
+
+int ltk_eval_alphas_timed(ltk_ctx* ctx, const double* d_alphas, int64_t B, double* d_lap, void* d_workspace,
+                          size_t workspace_bytes, void* stream, float* h_ms)
+{
+    if (!ctx) return LTK_E_ARG;
+    if (!d_alphas || !d_lap || !d_workspace || !h_ms || B < 1) return fail(ctx, LTK_E_ARG, "null or non-positive argument");
+    WsLayout w = ws_layout(ctx->ns, B, false);
+    if (workspace_bytes < w.total) return fail(ctx, LTK_E_WORKSPACE, "workspace too small (see ltk_workspace_bytes)");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaEvent_t ev[4];
+    for (int i = 0; i < 4; ++i) LTK_CUDA(ctx, cudaEventCreate(&ev[i]));
+    int rc = run_pipeline(ctx, d_alphas, nullptr, 0, B, d_lap, static_cast<char*>(d_workspace), w, false, st, ev);
+    if (rc == LTK_OK) {
+        cudaError_t e = cudaEventSynchronize(ev[3]);
+        for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaEventElapsedTime(&h_ms[i], ev[i], ev[i + 1]);
+        if (e != cudaSuccess) rc = fail(ctx, LTK_E_CUDA, "event timing", e);
+    }
+    for (int i = 0; i < 4; ++i) cudaEventDestroy(ev[i]);
+    return rc;
+}
+
+int ltk_topk_pairs(ltk_ctx* ctx, const double* d_lap, const int64_t* d_idx, int64_t count, int k, double* d_best_lap,
+                   int64_t* d_best_idx, void* stream)
+{
+    if (!ctx) return LTK_E_ARG;
+    if (!d_lap || !d_idx || !d_best_lap || !d_best_idx || count < 0) return fail(ctx, LTK_E_ARG, "null or negative argument");
+    if (k < 1 || k > TOPK_MAX) return fail(ctx, LTK_E_ARG, "k must be in 1..64");
+    DeviceGuard guard(ctx->device);
+    topk_select<<<1, TOPK_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+        d_lap, reinterpret_cast<const long long*>(d_idx), count, count < 1 ? 1 : count, 0, k, d_best_lap,
+        reinterpret_cast<long long*>(d_best_idx));
+    g_launches.fetch_add(1);
+    LTK_CUDA(ctx, cudaGetLastError());
+    return LTK_OK;
 }
 
 int ltk_eval_controls(ltk_ctx* ctx, const double* d_xy, int m, int64_t B, double* d_lap, void* d_workspace,

@@ -30,19 +30,21 @@ def merge_topk(laps, idx, k):
     return laps[order], idx[order]
 
 
-def allgather_topk(local_laps, local_idx, k, group=None):
-    """All-gather each rank's k best and merge; every rank returns the same (laps[k], idx[k])."""
+def allgather_topk(local_laps, local_idx, k, group=None, merge=merge_topk):
+    """All-gather each rank's k best and merge; every rank returns the same (laps[k], idx[k]).
+    `merge(laps, idx, k)` defaults to the torch implementation above; on the GPU pass
+    `LapTimeEvaluator.merge_topk_device` (ltk_topk_pairs kernel)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
-        return merge_topk(local_laps, local_idx, k)
+        return merge(local_laps, local_idx, k)
     # one collective: pack the f64 laps' bits and the i64 indices into a single int64 buffer
     packed = torch.cat([local_laps.contiguous().view(torch.int64), local_idx.contiguous()])
     gathered = torch.empty(world * packed.numel(), dtype=torch.int64, device=packed.device)
     dist.all_gather_into_tensor(gathered, packed, group=group)
     g = gathered.view(world, 2, -1)
     laps = g[:, 0, :].contiguous().view(torch.float64).reshape(-1)
-    idx = g[:, 1, :].reshape(-1)
-    return merge_topk(laps, idx, k)
+    idx = g[:, 1, :].reshape(-1).contiguous()
+    return merge(laps, idx, k)
 
 
 def sharded_population_topk(evaluator, local_alphas, index_base, k, group=None):
@@ -50,5 +52,5 @@ def sharded_population_topk(evaluator, local_alphas, index_base, k, group=None):
     Returns (local_laps [B_local] CUDA, best_laps[k], best_idx[k])."""
     d_lap = evaluator.lap_times_device(local_alphas)
     best, idx = evaluator.topk_device(d_lap, k, index_base=index_base)
-    g_best, g_idx = allgather_topk(best, idx, k, group)
+    g_best, g_idx = allgather_topk(best, idx, k, group, merge=evaluator.merge_topk_device)
     return d_lap, g_best, g_idx

@@ -99,6 +99,30 @@ class LapTimeEvaluator:
             _native.check(rc, self._ctx)
         return out
 
+    def kernel_times(self, alphas, out, reps=5):
+        """Average CUDA-event duration (ms) of each pipeline kernel over `reps` passes (measurement hook)."""
+        B = alphas.shape[0]
+        ws = self._workspace(B)
+        ms = (C.c_float * 3)()
+        acc = np.zeros(3)
+        for _ in range(reps):
+            rc = self.lib.ltk_eval_alphas_timed(self._ctx, _device.ptr(alphas), B, _device.ptr(out), _device.ptr(ws),
+                                                ws.numel(), _device.stream_ptr(self.torch, self.device), ms)
+            _native.check(rc, self._ctx)
+            acc += np.array(ms[:])
+        acc /= reps
+        return {"k1_curvature": float(acc[0]), "k2_forward": float(acc[1]), "k3_backward": float(acc[2])}
+
+    def merge_topk_device(self, laps, idx, k=DEFAULT_TOPK):
+        """Stable ascending top-k of explicit (lap, global index) pairs (the multi-GPU merge)."""
+        torch = self.torch
+        best = torch.empty(k, dtype=torch.float64, device=self.device)
+        out_idx = torch.empty(k, dtype=torch.int64, device=self.device)
+        rc = self.lib.ltk_topk_pairs(self._ctx, _device.ptr(laps), _device.ptr(idx), laps.numel(), int(k),
+                                     _device.ptr(best), _device.ptr(out_idx), _device.stream_ptr(torch, self.device))
+        _native.check(rc, self._ctx)
+        return best, out_idx
+
     def controls_lap_times_device(self, xy, out=None):
         """xy: float64 CUDA tensor [B, 2, n_alpha + 1] of control points (calcMinTime surface)."""
         torch = self.torch

@@ -1,0 +1,286 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI (ctypes facade), against
+  (a) the golden vectors of the unmodified reference,
+  (b) the level-2 C oracle on identical inputs -- bit for bit, at BASELINE.json's full size,
+  (c) size-independent properties (idempotence, permutation / chunking invariance, ragged batches).
+Tolerances (fp64): CUDA == C oracle exactly; lap vs reference <= 1e-9 relative on the BASELINE
+populations except the documented friction-circle noise floor (DESIGN.md "Parity")."""
+import numpy as np
+import pytest
+import torch
+
+import lap_time_optimization_b200 as ltk
+from conftest import case_setup, golden_cases, rel_err
+from oracle import c_oracle
+from oracle.reference_port import OracleTrack, load_vehicle, top_k
+
+pytestmark = pytest.mark.gpu
+PROFILE_KEYS = ("k", "v_local", "v_acclim", "v_declim", "v")
+
+
+def make(name, ns=None):
+    tj, width, vj, mode = case_setup(name)
+    track = ltk.Track(tj, track_width=width, quiet=True)
+    ev = ltk.LapTimeEvaluator(track, ltk.load_vehicle(vj), mode, ns)
+    co = c_oracle.COracle(OracleTrack(tj, width), load_vehicle(vj), mode, ns, device_sum_order=True)
+    return ev, co
+
+
+@pytest.fixture(scope="module")
+def buckmore():
+    ev, co = make("buckmore_tbr18_bayes")
+    yield ev, co
+    ev.close()
+
+
+# ---- (a)+(b): every golden case ------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_cases())
+def test_golden_case(name, golden):
+    g = golden(name)
+    ev, co = make(name, int(g["ns"]))
+    laps = ev.lap_times(g["alphas"])
+    assert np.array_equal(laps, co.lap_times(g["alphas"])), "CUDA differs from the C oracle"
+    rel = rel_err(laps, g["laps"])
+    if "mx5" in name:
+        assert rel.max() <= 1e-13
+    elif "full" in name:
+        assert np.median(rel) <= 1e-9 and rel.max() <= 1e-7  # zig-zag lines: see tests/test_oracle.py
+    else:
+        assert np.median(rel) <= 1e-10 and rel.max() <= 1e-9
+    for i in range(int(g["n_profiles"])):
+        pr, cp = ev.profile(g["alphas"][i]), co.profile(g["alphas"][i])
+        for key in PROFILE_KEYS:
+            assert np.array_equal(pr[key], cp[key]), key
+        assert pr["lap"] == laps[i] and pr["length"] == g["prof_length"][i]
+        assert np.array_equal(pr["s"], g["prof_s"][i])
+        assert np.max(np.abs(pr["k"] - g["prof_k"][i])) <= 1e-12 * np.max(g["prof_k"][i])
+    ev.close()
+
+
+# ---- staged parity: sweeps fed the REFERENCE's curvature -----------------------------------------
+@pytest.mark.parametrize("name", ["buckmore_tbr18_bayes", "buckmore_mx5_bayes", "gyg_tbr18_bayes", "clay_mx5_full"])
+def test_velocity_profile_given_reference_curvature(name, golden):
+    g = golden(name)
+    _, _, vj, _ = case_setup(name)
+    veh = ltk.load_vehicle(vj)
+    exact = total = 0
+    for i in range(int(g["n_profiles"])):
+        s = g["prof_s"][i]
+        vp = ltk.VelocityProfile(veh, s[:-1], g["prof_k"][i], g["prof_length"][i])
+        assert np.array_equal(vp.v_local, g["prof_v_local"][i])
+        for key, ours in (("v_acclim", vp.v_acclim), ("v_declim", vp.v_declim), ("v", vp.v)):
+            # x*x vs libm pow(x,2) differ by one ulp in ~0.08 % of squares (oracle/lap_oracle.c sq())
+            assert np.max(rel_err(ours, g["prof_" + key][i])) <= 1e-12
+            exact += int(np.sum(ours == g["prof_" + key][i]))
+            total += ours.size
+        lap = np.sum(np.diff(s) / vp.v)
+        assert abs(lap - g["prof_lap"][i]) <= 1e-13 * lap
+    assert exact >= 0.99 * total
+
+
+def test_velocity_profile_open_path(golden):
+    """s_max=None skips the wrap step (velocity.py:42-43, :66-67); checked against the Python port."""
+    from oracle.reference_port import velocity_profile
+
+    g = golden("buckmore_tbr18_bayes")
+    veh = ltk.load_vehicle(ltk.data_path("vehicles", "tbr18.json"))
+    oveh = load_vehicle(ltk.data_path("vehicles", "tbr18.json"))
+    s, k = g["prof_s"][1][:-1], g["prof_k"][1]
+    ref = velocity_profile(oveh, s, k, None)
+    vp = ltk.VelocityProfile(veh, s, k, None)
+    for ours, theirs in zip((vp.v_local, vp.v_acclim, vp.v_declim, vp.v), ref):
+        assert np.max(rel_err(ours, theirs)) <= 1e-12
+
+
+# ---- Path facade ----------------------------------------------------------------------------------
+def test_path_facade(golden):
+    g = golden("buckmore_tbr18_bayes")
+    c = g["prof_controls"][0].copy()
+    p = ltk.Path(c, True)
+    s = g["prof_s"][0]
+    k = p.curvature(s[:-1])
+    assert np.max(np.abs(k - g["prof_k"][0])) <= 1e-12 * np.max(g["prof_k"][0])
+    ks = p.curvature(s[:-1], return_absolute_value=False)
+    assert np.array_equal(np.abs(ks), k) and (ks < 0).any() and (ks > 0).any()
+    assert abs(p.gamma2(s[:-1]) - np.sum(g["prof_k"][0] ** 2)) <= 1e-11 * np.sum(g["prof_k"][0] ** 2)
+    xy = p.position(p.dists[:-1])  # the spline interpolates its control points
+    assert np.max(np.abs(xy - c[:, :-1])) <= 1e-10
+    assert p.position() is c
+    # the facade kernel and the batched K1 kernel build the same spline
+    ev, _ = make("buckmore_tbr18_bayes")
+    assert np.array_equal(ev.profile(g["alphas"][0])["k"], k)
+    ev.close()
+
+
+# ---- full BASELINE.json size ------------------------------------------------------------------------
+@pytest.mark.parametrize("veh", ["tbr18", "mx5"])
+def test_full_size_population_bit_exact_and_topk(veh):
+    ev, co = make(f"buckmore_{veh}_bayes")
+    B = 65536
+    a = np.random.default_rng(1002).uniform(0.0, 0.99, (B, ev.n_alpha))
+    d_lap = ev.lap_times_device(torch.as_tensor(a).cuda())
+    laps = d_lap.cpu().numpy()
+    ref = co.lap_times(a)
+    assert np.array_equal(laps, ref)
+    best, idx = ev.topk(d_lap, 10)
+    o_idx, o_best = top_k(list(ref), 10)
+    assert np.array_equal(idx, o_idx) and np.array_equal(best, o_best)
+    assert np.all(np.diff(best) >= 0) and np.isfinite(laps).all()
+    assert 40.0 < laps.min() and laps.max() < 80.0
+    ev.close()
+
+
+def test_reference_port_sample_within_tolerance(buckmore):
+    """End to end against the reference-equivalent Python port on fresh random candidates."""
+    from oracle.reference_port import OracleEvaluator
+
+    ev, _ = buckmore
+    tj, width, vj, mode = case_setup("buckmore_tbr18_bayes")
+    port = OracleEvaluator(OracleTrack(tj, width), load_vehicle(vj), mode)
+    a = np.random.default_rng(77).uniform(0.0, 0.99, (96, ev.n_alpha))
+    rel = rel_err(ev.lap_times(a), [port.lap_time(x) for x in a])
+    assert np.median(rel) <= 1e-10 and rel.max() <= 1e-9
+
+
+# ---- properties ----------------------------------------------------------------------------------------
+def test_idempotent_and_permutation_invariant(buckmore):
+    ev, _ = buckmore
+    a = np.random.default_rng(5).uniform(0.0, 0.99, (5000, ev.n_alpha))
+    l1, l2 = ev.lap_times(a), ev.lap_times(a)
+    assert np.array_equal(l1, l2)
+    perm = np.random.default_rng(6).permutation(len(a))
+    assert np.array_equal(ev.lap_times(a[perm]), l1[perm])
+
+
+@pytest.mark.parametrize("B", [1, 2, 31, 32, 33, 63, 65, 1000])
+def test_ragged_batches(buckmore, B):
+    ev, co = buckmore
+    a = np.random.default_rng(B).uniform(0.0, 0.99, (B, ev.n_alpha))
+    assert np.array_equal(ev.lap_times(a), co.lap_times(a))
+
+
+def test_empty_batch(buckmore):
+    ev, _ = buckmore
+    out = ev.lap_times_device(torch.empty((0, ev.n_alpha), dtype=torch.float64, device="cuda"))
+    assert out.numel() == 0
+
+
+def test_chunking_invariance():
+    ev, _ = make("buckmore_tbr18_bayes")
+    a = np.random.default_rng(9).uniform(0.0, 0.99, (20000, ev.n_alpha))
+    whole = ev.lap_times(a)
+    ev.max_workspace_bytes = ev.workspace_bytes(4096)  # forces 5 chunks
+    assert ev.max_batch() == 4096
+    assert np.array_equal(ev.lap_times(a), whole)
+    ev.close()
+
+
+def test_controls_entry_point_equals_alpha_entry_point(buckmore, golden):
+    ev, _ = buckmore
+    g = golden("buckmore_tbr18_bayes")
+    a = g["alphas"][:64]
+    xy = np.stack([ev.track.control_points_bayesian(x) for x in a])  # [B, 2, 44]; last column ignored
+    laps_c = ev.controls_lap_times_device(torch.as_tensor(xy).cuda()).cpu().numpy()
+    assert np.array_equal(laps_c, ev.lap_times(a))
+
+
+def test_alpha_outside_unit_box_is_not_clamped(buckmore):
+    ev, co = buckmore
+    a = np.random.default_rng(3).uniform(-0.46, 1.97, (256, ev.n_alpha))  # COBYLA range, SURVEY.md section 6
+    laps = ev.lap_times(a)
+    assert np.array_equal(laps, co.lap_times(a)) and np.isfinite(laps).all()
+
+
+def test_ns_override(buckmore, golden):
+    ev, _ = make("buckmore_tbr18_bayes")
+    a0 = np.random.default_rng(0).uniform(0, 0.99, 43)
+    assert rel_err(ev.lap_times(a0), 45.16138534803076) <= 1e-9
+    ev.set_ns(2501)
+    assert rel_err(ev.lap_times(a0), 44.94242820684669) <= 1e-9
+    ev.set_ns(10001)
+    assert rel_err(ev.lap_times(a0), 44.87309090019508) <= 1e-9
+    ev.close()
+
+
+# ---- top-k ---------------------------------------------------------------------------------------------
+def test_topk_ties_nan_and_short_input(buckmore):
+    ev, _ = buckmore
+    laps = np.array([3.0, 1.0, np.nan, 1.0, 2.0, 1.0, 7.0])
+    best, idx = ev.topk(laps, 5, index_base=100)
+    assert idx.tolist() == [101, 103, 105, 104, 100] and best.tolist() == [1.0, 1.0, 1.0, 2.0, 3.0]
+    best, idx = ev.topk(np.array([5.0, 4.0]), 4)
+    assert idx.tolist() == [1, 0, -1, -1] and np.isinf(best[2:]).all()
+    rng = np.random.default_rng(2)
+    big = rng.integers(0, 50, 300000).astype(np.float64)  # heavy ties across blocks
+    best, idx = ev.topk(big, 64)
+    o_idx, o_best = top_k(list(big), 64)
+    assert np.array_equal(idx, o_idx) and np.array_equal(best, o_best)
+
+
+def test_merge_pairs_kernel(buckmore):
+    ev, _ = buckmore
+    laps = torch.tensor([2.0, 1.0, 1.0, float("nan"), 3.0, 0.5, 9.0], dtype=torch.float64, device="cuda")
+    idx = torch.tensor([7, 9, 4, 1, 2, -1, 3], dtype=torch.int64, device="cuda")
+    b, i = ev.merge_topk_device(laps, idx, 4)
+    assert i.tolist() == [4, 9, 7, 2] and b.tolist() == [1.0, 1.0, 2.0, 3.0]
+
+
+def test_sharded_population_topk_single_rank(buckmore):
+    from lap_time_optimization_b200.distributed import shard_bounds, sharded_population_topk
+
+    ev, co = buckmore
+    a = np.random.default_rng(21).uniform(0.0, 0.99, (3000, ev.n_alpha))
+    ref = co.lap_times(a)
+    # emulate 3 ranks on one GPU: shard, local top-k with global indices, merge
+    pieces = []
+    for r in range(3):
+        lo, hi = shard_bounds(len(a), r, 3)
+        _, b, i = sharded_population_topk(ev, torch.as_tensor(a[lo:hi]).cuda(), lo, 10)
+        pieces.append((b, i))
+    b, i = ev.merge_topk_device(torch.cat([p[0] for p in pieces]), torch.cat([p[1] for p in pieces]), 10)
+    o_idx, o_best = top_k(list(ref), 10)
+    assert np.array_equal(i.cpu().numpy(), o_idx) and np.array_equal(b.cpu().numpy(), o_best)
+
+
+# ---- the reference's call surface -------------------------------------------------------------------------
+def test_trajectory_facades(golden):
+    g = golden("buckmore_tbr18_full")
+    track = ltk.Track(ltk.data_path("tracks", "buckmore.json"), track_width=0.8, quiet=True)
+    veh = ltk.load_vehicle(ltk.data_path("vehicles", "tbr18.json"))
+    T = ltk.Trajectory(track, veh)
+    T.update(g["alphas"][0])  # centre line
+    T.update_velocity()
+    assert rel_err(T.lap_time(), 47.03786396842785) <= 1e-9
+    assert np.array_equal(T.s, g["prof_s"][0]) and T.path.length == g["prof_length"][0]
+    assert np.max(rel_err(T.velocity.v, g["prof_v"][0])) <= 1e-6
+    assert np.max(rel_err(T.velocity.v_local, g["prof_v_local"][0])) <= 1e-11
+    assert rel_err(np.sum(np.diff(T.s) / T.velocity.v), T.lap_time()) <= 1e-14
+    assert np.max(rel_err(T.lap_time_batch(g["alphas"][:8]), g["laps"][:8])) <= 1e-7
+
+    gb = golden("buckmore_tbr18_bayes")
+    TB = ltk.TrajectoryBayesianNonlinear(track, veh)
+    for i in (0, 5, 6):
+        lap = TB.calcMinTime(TB.updateAlphas(gb["alphas"][i]))
+        assert rel_err(lap, gb["laps"][i]) <= 1e-9 and TB.lap_time() == lap
+    assert TB.path.length > 0 and TB.velocity.v.shape == (846,)
+    laps, best, idx = TB.population_topk(gb["alphas"], 10)
+    o_idx, _ = top_k(list(gb["laps"]), 10)
+    assert np.array_equal(idx, o_idx)
+    assert TB.random_population(7, seed=1).shape == (7, 43)
+
+
+def test_errors(buckmore):
+    ev, _ = buckmore
+    with pytest.raises(ValueError):
+        ev.lap_times_device(torch.zeros((4, 5), dtype=torch.float64, device="cuda"))
+    with pytest.raises(ValueError):
+        ev.lap_times_device(torch.zeros((4, ev.n_alpha), dtype=torch.float32, device="cuda"))
+    import ctypes as C
+    from lap_time_optimization_b200 import _device, _native
+
+    a = torch.zeros((64, ev.n_alpha), dtype=torch.float64, device="cuda")
+    out = torch.empty(64, dtype=torch.float64, device="cuda")
+    ws = torch.empty(1024, dtype=torch.uint8, device="cuda")
+    rc = ev.lib.ltk_eval_alphas(ev._ctx, _device.ptr(a), 64, _device.ptr(out), _device.ptr(ws), ws.numel(), None)
+    assert rc == _native.LTK_E_WORKSPACE and b"workspace" in ev.lib.ltk_last_error(ev._ctx)
+    with pytest.raises(ltk.LtkError):
+        ev.topk(np.zeros(4), 65)

@@ -1,0 +1,159 @@
+"""CPU: host-side logic (track / vehicle loaders, facade bookkeeping, C-ABI surface, multi-rank
+top-k merge over gloo).  No kernel is launched here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import lap_time_optimization_b200 as ltk
+from conftest import ROOT
+from lap_time_optimization_b200 import _native
+from lap_time_optimization_b200.distributed import allgather_topk, merge_topk, shard_bounds
+from oracle import c_oracle
+from oracle.reference_port import OracleTrack, load_vehicle
+
+TRACKS = ["buckmore", "clay", "gyg", "whilton"]
+
+
+@pytest.mark.parametrize("name", TRACKS)
+@pytest.mark.parametrize("width", [0.8, 0.6, 1.0, 5.0, 0.0])
+def test_track_matches_oracle_loader(name, width):
+    tj = ltk.data_path("tracks", name + ".json")
+    t, o = ltk.Track(tj, track_width=width, quiet=True), OracleTrack(tj, width)
+    assert t.closed == o.closed and t.size == o.size and t.length == o.length
+    for a, b in ((t.left, o.left), (t.right, o.right), (t.diffs, o.diffs), (t.left_decongested, o.left_d),
+                 (t.diffs_decongested, o.diffs_d)):
+        assert np.array_equal(a, b)
+    rng = np.random.default_rng(5)
+    a_full, a_bayes = rng.uniform(-0.5, 1.5, t.size), rng.uniform(0, 0.99, o.left_d.shape[1] - 1)
+    assert np.array_equal(t.control_points(a_full), o.control_points(a_full))
+    assert np.array_equal(t.control_points_bayesian(a_bayes), o.control_points_bayesian(a_bayes))
+    left, diff = t.affine_map("bayes")
+    assert left.shape == (2, o.left_d.shape[1] - 1) and left.flags.c_contiguous and diff.flags.c_contiguous
+
+
+def test_track_sizes():
+    n = {nm: ltk.Track(ltk.data_path("tracks", nm + ".json"), track_width=0.8, quiet=True) for nm in TRACKS}
+    assert [n[k].left_decongested.shape[1] for k in TRACKS] == [44, 46, 40, 51]
+    assert n["buckmore"].size == 131 and int(np.ceil(n["buckmore"].length)) == 847
+
+
+@pytest.mark.parametrize("veh", ["tbr18.json", "MX5.json"])
+def test_vehicle_constants_match_oracle(veh):
+    vj = ltk.data_path("vehicles", veh)
+    ours, theirs = ltk.load_vehicle(vj).to_ltk(), c_oracle.vehicle_struct(load_vehicle(vj))
+    for f in ("kind", "n_map", "mass", "mu_g", "f_max", "f_max_sq", "e0", "cr2"):
+        assert getattr(ours, f) == getattr(theirs, f), f
+    assert list(ours.map_v) == list(theirs.map_v) and list(ours.map_f) == list(theirs.map_f)
+
+
+def test_vehicle_callbacks():
+    v, o = ltk.load_vehicle(ltk.data_path("vehicles", "tbr18.json")), load_vehicle(ltk.data_path("vehicles", "tbr18.json"))
+    m, om = ltk.load_vehicle(ltk.data_path("vehicles", "MX5.json")), load_vehicle(ltk.data_path("vehicles", "MX5.json"))
+    for vel in (0.0, 5.0, 7.3, 19.999, 35.0, 60.0):
+        assert v.engine_force(vel) == o.engine_force(vel) and m.engine_force(vel) == om.engine_force(vel)
+        for k in (0.0, 0.01, 0.3):
+            assert v.traction(np.float64(vel), k) == o.traction(np.float64(vel), k)
+            assert m.traction(np.float64(vel), k) == om.traction(np.float64(vel), k)
+    assert isinstance(m, ltk.VehicleMX5) and m.friction_coef == 1.5 and v.friction_coef == 1.5
+
+
+def test_path_host_attributes_and_closure_quirk():
+    t = ltk.Track(ltk.data_path("tracks", "buckmore.json"), track_width=0.8, quiet=True)
+    a = np.random.default_rng(0).uniform(0, 0.99, 43)
+    c = t.control_points_bayesian(a)
+    before = c.copy()
+    p = ltk.Path(c, True)
+    assert np.array_equal(p.dists, np.append(0, np.cumsum(np.linalg.norm(np.diff(before, axis=1), axis=0))))
+    assert p.length == p.dists[-1]
+    # like splprep(per=1): the caller's last column now equals the first
+    assert np.array_equal(c[:, -1], c[:, 0]) and not np.array_equal(before[:, -1], before[:, 0])
+    assert p.controls is c
+    with pytest.raises(AttributeError):
+        p.spline
+
+
+def test_abi_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "ltk.h")).read()
+    declared = sorted(set(re.findall(r"\b(ltk_[a-z_0-9]+)\s*\(", header)))
+    assert len(declared) >= 14
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"libltk.so does not export {name}"
+    assert sorted(_native.SIGNATURES) == declared
+    assert _native.load().ltk_version() >= 100
+    assert ctypes.sizeof(_native.LtkVehicle) == 8 + 8 * 4 + 2 * 8 * 16 + 16
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback_without_gpu():
+    t = ltk.Track(ltk.data_path("tracks", "buckmore.json"), track_width=0.8, quiet=True)
+    v = ltk.load_vehicle(ltk.data_path("vehicles", "tbr18.json"))
+    with pytest.raises(ltk.LtkUnavailable):
+        ltk.LapTimeEvaluator(t, v)
+    with pytest.raises(ltk.LtkUnavailable):
+        ltk.Path(t.control_points(np.full(t.size, 0.5)), True).curvature(np.array([0.0, 1.0]))
+    # the raw ABI reports an error code, it does not compute
+    lib = _native.load()
+    h = ctypes.c_void_p()
+    left, diff = t.affine_map("bayes")
+    dp = ctypes.POINTER(ctypes.c_double)
+    veh = v.to_ltk()
+    rc = lib.ltk_create(ctypes.byref(h), 0, left.ctypes.data_as(dp), diff.ctypes.data_as(dp), left.shape[1],
+                        ctypes.byref(veh), 847)
+    assert rc < 0 and lib.ltk_last_error(None)
+
+
+def test_shard_bounds_cover_everything():
+    for total in (0, 1, 10, 65536, 1048577):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_merge_topk_is_stable_and_handles_padding():
+    laps = torch.tensor([2.0, 1.0, 1.0, float("nan"), 3.0, 0.5, 9.0], dtype=torch.float64)
+    idx = torch.tensor([7, 9, 4, 1, 2, -1, 3], dtype=torch.int64)
+    b, i = merge_topk(laps, idx, 4)
+    assert i.tolist() == [4, 9, 7, 2] and b.tolist() == [1.0, 1.0, 2.0, 3.0]
+
+
+def _gloo_worker(rank, world, port, k, q):
+    import torch.distributed as dist
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    rng = np.random.default_rng(11)
+    laps_all = rng.uniform(40, 50, 1000)
+    laps_all[17] = laps_all[900] = 39.0  # a tie across ranks: the lower global index must come first
+    lo, hi = shard_bounds(1000, rank, world)
+    local = torch.tensor(laps_all[lo:hi])
+    order = torch.sort(local, stable=True).indices[:k]
+    best, idx = allgather_topk(local[order], order + lo, k)
+    q.put((rank, best.tolist(), idx.tolist()))
+    dist.destroy_process_group()
+
+
+def test_allgather_topk_gloo_world2():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, 10, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+    rng = np.random.default_rng(11)
+    laps_all = rng.uniform(40, 50, 1000)
+    laps_all[17] = laps_all[900] = 39.0
+    expect = sorted(range(1000), key=lambda i: laps_all[i])[:10]
+    assert out[0][2] == expect and out[1][2] == expect and out[0][1] == out[1][1]
+    assert expect[:2] == [17, 900]
