@@ -70,18 +70,25 @@ VehDev make_vehdev(const ltk_vehicle& v)
     d.kind = v.kind;
     d.n_map = v.n_map;
     d.mass = v.mass;
+    d.inv_mass = 1.0 / v.mass;  // correctly rounded; see div_by_const
     d.mu_g = v.mu_g;
     d.f_max = v.f_max;
     d.f_max_sq = v.f_max_sq;
     d.e0 = v.e0;
     d.cr2 = v.cr2;
-    for (int i = 0; i < LTK_MAX_ENGINE_MAP; ++i) {
-        d.map_v[i] = v.map_v[i];
-        d.map_f[i] = v.map_f[i];
+    for (int i = 0; i < LTK_MAX_ENGINE_MAP; ++i) d.thr[i] = 0x7fffffffffffffffLL;
+    if (v.kind == 0) {
+        const int n = v.n_map;
+        for (int i = 0; i < n; ++i) memcpy(&d.thr[i], &v.map_v[i], sizeof(double));
+        // extended segment table, see VehDev; slopes exactly as np.interp forms them
+        d.ext_b[0] = v.map_v[0]; d.ext_f[0] = v.map_f[0]; d.ext_s[0] = 0.0;
+        for (int j = 1; j < n; ++j) {
+            d.ext_b[j] = v.map_v[j - 1];
+            d.ext_f[j] = v.map_f[j - 1];
+            d.ext_s[j] = (v.map_f[j] - v.map_f[j - 1]) / (v.map_v[j] - v.map_v[j - 1]);
+        }
+        d.ext_b[n] = v.map_v[n - 1]; d.ext_f[n] = v.map_f[n - 1]; d.ext_s[n] = 0.0;
     }
-    // slope of each engine-map segment exactly as np.interp forms it: (f[j+1]-f[j])/(v[j+1]-v[j])
-    for (int i = 0; i + 1 < v.n_map && i + 1 < LTK_MAX_ENGINE_MAP; ++i)
-        d.map_s[i] = (v.map_f[i + 1] - v.map_f[i]) / (v.map_v[i + 1] - v.map_v[i]);
     return d;
 }
 
@@ -90,6 +97,11 @@ int check_vehicle(const ltk_vehicle* v)
     if (!v) return 0;
     if (v->kind != 0 && v->kind != 1) return 0;
     if (v->kind == 0 && (v->n_map < 2 || v->n_map > LTK_MAX_ENGINE_MAP)) return 0;
+    if (v->kind == 0)
+        for (int i = 0; i < v->n_map; ++i) {
+            if (!(v->map_v[i] >= 0.0)) return 0;                      // integer-ordered comparison needs x >= 0
+            if (i > 0 && !(v->map_v[i] > v->map_v[i - 1])) return 0;  // np.interp needs increasing abscissae
+        }
     if (!(v->mass > 0.0)) return 0;
     return 1;
 }
@@ -180,8 +192,12 @@ int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m
     s.vmin = dumps ? reinterpret_cast<double*>(ws + w.vmin_off) : nullptr;
     s.ns = ctx->ns; s.B = B; s.Bp = w.Bp;
     unsigned grid = (unsigned)((B + SWEEP_THREADS - 1) / SWEEP_THREADS);
-    if (ctx->veh.kind == 0) k2_forward<0><<<grid, SWEEP_THREADS, 0, st>>>(s, ctx->veh);
-    else k2_forward<1><<<grid, SWEEP_THREADS, 0, st>>>(s, ctx->veh);
+    if (ctx->veh.kind == 0) {
+        if (ctx->veh.n_map <= 8) k2_forward<0, 8><<<grid, SWEEP_THREADS, 0, st>>>(s, ctx->veh);
+        else k2_forward<0, 16><<<grid, SWEEP_THREADS, 0, st>>>(s, ctx->veh);
+    } else {
+        k2_forward<1, 8><<<grid, SWEEP_THREADS, 0, st>>>(s, ctx->veh);
+    }
     if (ev) LTK_CUDA(ctx, cudaEventRecord(ev[2], st));
     if (ctx->veh.kind == 0) k3_backward<0><<<grid, SWEEP_THREADS, 0, st>>>(s, ctx->veh);
     else k3_backward<1><<<grid, SWEEP_THREADS, 0, st>>>(s, ctx->veh);

@@ -82,8 +82,9 @@ class LapTimeEvaluator:
         """alphas: float64 CUDA tensor [B, n_alpha] (contiguous) -> float64 CUDA tensor [B].
         Asynchronous on the current stream."""
         torch = self.torch
-        if alphas.dtype != torch.float64 or not alphas.is_cuda or not alphas.is_contiguous():
-            raise ValueError("alphas must be a contiguous float64 CUDA tensor")
+        if alphas.dtype != torch.float64 or not alphas.is_cuda:
+            raise ValueError("alphas must be a float64 CUDA tensor")
+        alphas = alphas.contiguous()
         if alphas.dim() != 2 or alphas.shape[1] != self.n_alpha:
             raise ValueError(f"alphas must be [B, {self.n_alpha}]")
         B = alphas.shape[0]
@@ -126,8 +127,9 @@ class LapTimeEvaluator:
     def controls_lap_times_device(self, xy, out=None):
         """xy: float64 CUDA tensor [B, 2, n_alpha + 1] of control points (calcMinTime surface)."""
         torch = self.torch
-        if xy.dtype != torch.float64 or not xy.is_cuda or not xy.is_contiguous():
-            raise ValueError("controls must be a contiguous float64 CUDA tensor")
+        if xy.dtype != torch.float64 or not xy.is_cuda:
+            raise ValueError("controls must be a float64 CUDA tensor")
+        xy = xy.contiguous()
         if xy.dim() != 3 or xy.shape[1] != 2 or xy.shape[2] != self.n_alpha + 1:
             raise ValueError(f"controls must be [B, 2, {self.n_alpha + 1}]")
         B = xy.shape[0]
