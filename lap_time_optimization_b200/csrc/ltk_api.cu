@@ -108,10 +108,10 @@ int check_vehicle(const ltk_vehicle* v)
 
 struct WsLayout {
     long long Bp;
-    size_t kap_off, vacc_off, len_off, rot_off, vdec_off, vmin_off, total;
+    size_t kap_off, vacc_off, len_off, rot_off, mx_off, my_off, vdec_off, vmin_off, total;
 };
 
-WsLayout ws_layout(int ns, long long B, bool dumps)
+WsLayout ws_layout(int ns, int N, long long B, bool dumps)
 {
     WsLayout w;
     w.Bp = round_up(B < 1 ? 1 : B, 32);
@@ -122,6 +122,8 @@ WsLayout ws_layout(int ns, long long B, bool dumps)
     w.vacc_off = off; off += arr;
     w.len_off = off; off += (size_t)w.Bp * sizeof(double);
     w.rot_off = off; off += round_up((long long)w.Bp * sizeof(int), 256);
+    w.mx_off = off; off += (size_t)N * (size_t)w.Bp * sizeof(double);
+    w.my_off = off; off += (size_t)N * (size_t)w.Bp * sizeof(double);
     w.vdec_off = w.vmin_off = 0;
     if (dumps) {
         w.vdec_off = off; off += arr;
@@ -136,6 +138,8 @@ struct K1Config {
     size_t smem;
 };
 
+int k1a_threads(const ltk_ctx* ctx);
+
 bool pick_k1(const ltk_ctx* ctx, K1Config* out)
 {
     const int cand_g[2] = {16, 8};
@@ -145,7 +149,7 @@ bool pick_k1(const ltk_ctx* ctx, K1Config* out)
             int G = cand_g[gi];
             if (ctx->k1_g_override > 0 && G != ctx->k1_g_override) continue;
             size_t s = k1_smem_bytes(G, ctx->N, ctx->ns, staged);
-            if (s <= ctx->smem_optin) {
+            if (s <= ctx->smem_optin && k1a_threads(ctx) >= 32) {
                 out->G = G; out->staged = staged; out->smem = s;
                 return true;
             }
@@ -154,13 +158,34 @@ bool pick_k1(const ltk_ctx* ctx, K1Config* out)
     return false;
 }
 
-template <int G>
-cudaError_t launch_k1(const K1Args& a, size_t smem, cudaStream_t st)
+// threads per CTA of the solve kernel: its scratch is 4 doubles per (row, thread)
+int k1a_threads(const ltk_ctx* ctx)
 {
-    cudaError_t e = cudaFuncSetAttribute(k1_curvature<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    size_t per_thread = (size_t)4 * ctx->N * sizeof(double);
+    long long t = (long long)(ctx->smem_optin / per_thread) / 32 * 32;
+    if (t > 128) t = 128;
+    return (int)t;  // 0: does not fit
+}
+
+cudaError_t launch_k1a(const ltk_ctx* ctx, const K1Args& a, cudaStream_t st)
+{
+    int T = k1a_threads(ctx);
+    size_t smem = (size_t)4 * ctx->N * T * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(k1a_spline_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    unsigned grid = (unsigned)((a.Bp + T - 1) / T);
+    k1a_spline_solve<<<grid, T, smem, st>>>(a);
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
+}
+
+template <int G>
+cudaError_t launch_k1b(const K1Args& a, size_t smem, cudaStream_t st)
+{
+    cudaError_t e = cudaFuncSetAttribute(k1b_curvature<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     unsigned grid = (unsigned)(a.Bp / G);
-    k1_curvature<G><<<grid, K1_THREADS, smem, st>>>(a);
+    k1b_curvature<G><<<grid, K1_THREADS, smem, st>>>(a);
     g_launches.fetch_add(1);
     return cudaGetLastError();
 }
@@ -179,9 +204,12 @@ int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m
     a.kap = reinterpret_cast<double*>(ws + w.kap_off);
     a.rot = reinterpret_cast<int*>(ws + w.rot_off);
     a.len = reinterpret_cast<double*>(ws + w.len_off);
+    a.mx = reinterpret_cast<double*>(ws + w.mx_off);
+    a.my = reinterpret_cast<double*>(ws + w.my_off);
     a.staged = cfg.staged;
     if (ev) LTK_CUDA(ctx, cudaEventRecord(ev[0], st));
-    LTK_CUDA(ctx, cfg.G == 16 ? launch_k1<16>(a, cfg.smem, st) : launch_k1<8>(a, cfg.smem, st));
+    LTK_CUDA(ctx, launch_k1a(ctx, a, st));
+    LTK_CUDA(ctx, cfg.G == 16 ? launch_k1b<16>(a, cfg.smem, st) : launch_k1b<8>(a, cfg.smem, st));
     if (ev) LTK_CUDA(ctx, cudaEventRecord(ev[1], st));
 
     SweepArgs s;
@@ -295,7 +323,7 @@ int ltk_set_ns(ltk_ctx* ctx, int ns)
 int ltk_workspace_bytes(const ltk_ctx* ctx, int64_t B, size_t* out_bytes)
 {
     if (!ctx || !out_bytes || B < 0) return LTK_E_ARG;
-    *out_bytes = ws_layout(ctx->ns, B, false).total;
+    *out_bytes = ws_layout(ctx->ns, ctx->N, B, false).total;
     return LTK_OK;
 }
 
@@ -305,7 +333,7 @@ int ltk_eval_alphas(ltk_ctx* ctx, const double* d_alphas, int64_t B, double* d_l
     if (!ctx) return LTK_E_ARG;
     if (B == 0) return LTK_OK;
     if (!d_alphas || !d_lap || !d_workspace || B < 0) return fail(ctx, LTK_E_ARG, "null or negative argument");
-    WsLayout w = ws_layout(ctx->ns, B, false);
+    WsLayout w = ws_layout(ctx->ns, ctx->N, B, false);
     if (workspace_bytes < w.total) return fail(ctx, LTK_E_WORKSPACE, "workspace too small (see ltk_workspace_bytes)");
     DeviceGuard guard(ctx->device);
     return run_pipeline(ctx, d_alphas, nullptr, 0, B, d_lap, static_cast<char*>(d_workspace), w, false,
@@ -317,7 +345,7 @@ int ltk_eval_alphas_timed(ltk_ctx* ctx, const double* d_alphas, int64_t B, doubl
 {
     if (!ctx) return LTK_E_ARG;
     if (!d_alphas || !d_lap || !d_workspace || !h_ms || B < 1) return fail(ctx, LTK_E_ARG, "null or non-positive argument");
-    WsLayout w = ws_layout(ctx->ns, B, false);
+    WsLayout w = ws_layout(ctx->ns, ctx->N, B, false);
     if (workspace_bytes < w.total) return fail(ctx, LTK_E_WORKSPACE, "workspace too small (see ltk_workspace_bytes)");
     DeviceGuard guard(ctx->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -355,7 +383,7 @@ int ltk_eval_controls(ltk_ctx* ctx, const double* d_xy, int m, int64_t B, double
     if (B == 0) return LTK_OK;
     if (!d_xy || !d_lap || !d_workspace || B < 0) return fail(ctx, LTK_E_ARG, "null or negative argument");
     if (m != ctx->N + 1) return fail(ctx, LTK_E_ARG, "controls must have n_ctrl + 1 columns");
-    WsLayout w = ws_layout(ctx->ns, B, false);
+    WsLayout w = ws_layout(ctx->ns, ctx->N, B, false);
     if (workspace_bytes < w.total) return fail(ctx, LTK_E_WORKSPACE, "workspace too small (see ltk_workspace_bytes)");
     DeviceGuard guard(ctx->device);
     return run_pipeline(ctx, nullptr, d_xy, m, B, d_lap, static_cast<char*>(d_workspace), w, false,
@@ -369,7 +397,7 @@ int ltk_profile(ltk_ctx* ctx, const double* d_alpha, double* d_s, double* d_k, d
     if (!d_alpha) return fail(ctx, LTK_E_ARG, "null alpha");
     DeviceGuard guard(ctx->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    WsLayout w = ws_layout(ctx->ns, 1, true);
+    WsLayout w = ws_layout(ctx->ns, ctx->N, 1, true);
     size_t need = w.total + 256;
     if (ctx->profile_ws_bytes < need) {
         LTK_CUDA(ctx, cudaStreamSynchronize(st));

@@ -255,7 +255,8 @@ def test_trajectory_facades(golden):
     assert rel_err(T.lap_time(), 47.03786396842785) <= 1e-9
     assert np.array_equal(T.s, g["prof_s"][0]) and T.path.length == g["prof_length"][0]
     assert np.max(rel_err(T.velocity.v, g["prof_v"][0])) <= 1e-6
-    assert np.max(rel_err(T.velocity.v_local, g["prof_v_local"][0])) <= 1e-11
+    # v_local = sqrt(mu g / k) is ill-conditioned where the centre line is almost straight (k ~ 1e-5)
+    assert np.max(rel_err(T.velocity.v_local, g["prof_v_local"][0])) <= 1e-8
     assert rel_err(np.sum(np.diff(T.s) / T.velocity.v), T.lap_time()) <= 1e-14
     assert np.max(rel_err(T.lap_time_batch(g["alphas"][:8]), g["laps"][:8])) <= 1e-7
 
