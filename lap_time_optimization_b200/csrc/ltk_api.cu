@@ -25,7 +25,7 @@ struct ltk_ctx {
     long long* d_topk_idx;
     void* d_profile_ws;
     size_t profile_ws_bytes;
-    int k1_g_override, k1_staged_override;
+    int k1_g_override, k1_staged_override, k1_threads_override;
     char err[256];
 };
 
@@ -108,13 +108,13 @@ int check_vehicle(const ltk_vehicle* v)
 
 struct WsLayout {
     long long Bp;
-    size_t kap_off, vacc_off, len_off, rot_off, mx_off, my_off, vdec_off, vmin_off, total;
+    size_t kap_off, vacc_off, len_off, rot_off, mx_off, my_off, knots_off, vdec_off, vmin_off, total;
 };
 
 WsLayout ws_layout(int ns, int N, long long B, bool dumps)
 {
     WsLayout w;
-    w.Bp = round_up(B < 1 ? 1 : B, 32);
+    w.Bp = round_up(B < 1 ? 1 : B, 32);  // multiple of TILE and of the warp size
     size_t rows = (size_t)(ns - 1);
     size_t arr = rows * (size_t)w.Bp * sizeof(double);
     size_t off = 0;
@@ -124,6 +124,7 @@ WsLayout ws_layout(int ns, int N, long long B, bool dumps)
     w.rot_off = off; off += round_up((long long)w.Bp * sizeof(int), 256);
     w.mx_off = off; off += (size_t)N * (size_t)w.Bp * sizeof(double);
     w.my_off = off; off += (size_t)N * (size_t)w.Bp * sizeof(double);
+    w.knots_off = off; off += (size_t)(N + 1) * (size_t)w.Bp * sizeof(double);
     w.vdec_off = w.vmin_off = 0;
     if (dumps) {
         w.vdec_off = off; off += arr;
@@ -134,7 +135,7 @@ WsLayout ws_layout(int ns, int N, long long B, bool dumps)
 }
 
 struct K1Config {
-    int G, staged;
+    int G, threads, staged;
     size_t smem;
 };
 
@@ -148,9 +149,10 @@ bool pick_k1(const ltk_ctx* ctx, K1Config* out)
         for (int gi = 0; gi < 2; ++gi) {
             int G = cand_g[gi];
             if (ctx->k1_g_override > 0 && G != ctx->k1_g_override) continue;
-            size_t s = k1_smem_bytes(G, ctx->N, ctx->ns, staged);
+            int threads = ctx->k1_threads_override > 0 ? ctx->k1_threads_override : 512;
+            size_t s = k1_smem_bytes(G, threads, ctx->N, ctx->ns, staged);
             if (s <= ctx->smem_optin && k1a_threads(ctx) >= 32) {
-                out->G = G; out->staged = staged; out->smem = s;
+                out->G = G; out->threads = threads; out->staged = staged; out->smem = s;
                 return true;
             }
         }
@@ -179,15 +181,27 @@ cudaError_t launch_k1a(const ltk_ctx* ctx, const K1Args& a, cudaStream_t st)
     return cudaGetLastError();
 }
 
-template <int G>
+template <int G, int THREADS>
 cudaError_t launch_k1b(const K1Args& a, size_t smem, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(k1b_curvature<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k1b_curvature<G, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     unsigned grid = (unsigned)(a.Bp / G);
-    k1b_curvature<G><<<grid, K1_THREADS, smem, st>>>(a);
+    k1b_curvature<G, THREADS><<<grid, THREADS, smem, st>>>(a);
     g_launches.fetch_add(1);
     return cudaGetLastError();
+}
+
+cudaError_t launch_k1b_cfg(const K1Config& c, const K1Args& a, cudaStream_t st)
+{
+    if (c.G == 16) {
+        if (c.threads == 1024) return launch_k1b<16, 1024>(a, c.smem, st);
+        if (c.threads == 256) return launch_k1b<16, 256>(a, c.smem, st);
+        return launch_k1b<16, 512>(a, c.smem, st);
+    }
+    if (c.threads == 1024) return launch_k1b<8, 1024>(a, c.smem, st);
+    if (c.threads == 256) return launch_k1b<8, 256>(a, c.smem, st);
+    return launch_k1b<8, 512>(a, c.smem, st);
 }
 
 // the three pipeline launches on a laid-out workspace
@@ -206,10 +220,11 @@ int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m
     a.len = reinterpret_cast<double*>(ws + w.len_off);
     a.mx = reinterpret_cast<double*>(ws + w.mx_off);
     a.my = reinterpret_cast<double*>(ws + w.my_off);
+    a.knots = reinterpret_cast<double*>(ws + w.knots_off);
     a.staged = cfg.staged;
     if (ev) LTK_CUDA(ctx, cudaEventRecord(ev[0], st));
     LTK_CUDA(ctx, launch_k1a(ctx, a, st));
-    LTK_CUDA(ctx, cfg.G == 16 ? launch_k1b<16>(a, cfg.smem, st) : launch_k1b<8>(a, cfg.smem, st));
+    LTK_CUDA(ctx, launch_k1b_cfg(cfg, a, st));
     if (ev) LTK_CUDA(ctx, cudaEventRecord(ev[1], st));
 
     SweepArgs s;
@@ -274,6 +289,11 @@ int ltk_create(ltk_ctx** out, int device, const double* h_left_xy, const double*
     ctx->k1_staged_override = -1;
     if (const char* s = getenv("LTK_K1_G")) ctx->k1_g_override = atoi(s);
     if (const char* s = getenv("LTK_K1_STAGED")) ctx->k1_staged_override = atoi(s);
+    ctx->k1_threads_override = 0;
+    if (const char* s = getenv("LTK_K1_THREADS")) {
+        int t = atoi(s);
+        if (t == 256 || t == 512 || t == 1024) ctx->k1_threads_override = t;
+    }
     size_t bytes = sizeof(double) * 2 * (size_t)n_ctrl;
     if ((e = cudaMalloc(&ctx->d_left, bytes)) != cudaSuccess || (e = cudaMalloc(&ctx->d_diff, bytes)) != cudaSuccess ||
         (e = cudaMalloc(&ctx->d_topk_lap, sizeof(double) * TOPK_MAX_BLOCKS * TOPK_MAX)) != cudaSuccess ||
