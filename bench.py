@@ -260,10 +260,11 @@ def run_ours(args):
     if rank == 0:
         n = ns - 1
         peak, peak_src = hbm_peak()
-        alg = {"k1_curvature": 8 * na + 8 * n, "k2_forward": 16 * n, "k3_backward": 16 * n + 8}
+        alg = {"k1_curvature": 8 * na + 8 * n, "k2_forward": 16 * n, "k3_backward": 16 * n + 8,
+               "k23_sweep": 32 * n + 8}
         dom = max(kt, key=lambda k: kt[k])
         achieved = alg[dom] * B / (kt[dom] * 1e-3) / 1e9
-        a_staged = sum(alg.values())
+        a_staged = 8 * na + 40 * n + 8
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):

@@ -25,7 +25,7 @@ struct ltk_ctx {
     long long* d_topk_idx;
     void* d_profile_ws;
     size_t profile_ws_bytes;
-    int k1_g_override, k1_staged_override, k1_threads_override;
+    int k1_g_override, k1_staged_override, k1_threads_override, sweep_split;
     char err[256];
 };
 
@@ -108,7 +108,7 @@ int check_vehicle(const ltk_vehicle* v)
 
 struct WsLayout {
     long long Bp;
-    size_t kap_off, vacc_off, len_off, rot_off, mx_off, my_off, knots_off, vdec_off, vmin_off, total;
+    size_t kap_off, vacc_off, len_off, rot_off, mx_off, my_off, knots_off, vaccd_off, vdec_off, vmin_off, total;
 };
 
 WsLayout ws_layout(int ns, int N, long long B, bool dumps)
@@ -125,8 +125,9 @@ WsLayout ws_layout(int ns, int N, long long B, bool dumps)
     w.mx_off = off; off += (size_t)N * (size_t)w.Bp * sizeof(double);
     w.my_off = off; off += (size_t)N * (size_t)w.Bp * sizeof(double);
     w.knots_off = off; off += (size_t)(N + 1) * (size_t)w.Bp * sizeof(double);
-    w.vdec_off = w.vmin_off = 0;
+    w.vdec_off = w.vmin_off = w.vaccd_off = 0;
     if (dumps) {
+        w.vaccd_off = off; off += arr;
         w.vdec_off = off; off += arr;
         w.vmin_off = off; off += arr;
     }
@@ -227,25 +228,44 @@ int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m
     LTK_CUDA(ctx, launch_k1b_cfg(cfg, a, st));
     if (ev) LTK_CUDA(ctx, cudaEventRecord(ev[1], st));
 
-    SweepArgs s;
-    s.kap = a.kap;
-    s.vacc = reinterpret_cast<double*>(ws + w.vacc_off);
-    s.rot = a.rot; s.len = a.len; s.lap = d_lap;
-    s.vdec = dumps ? reinterpret_cast<double*>(ws + w.vdec_off) : nullptr;
-    s.vmin = dumps ? reinterpret_cast<double*>(ws + w.vmin_off) : nullptr;
-    s.ns = ctx->ns; s.B = B; s.Bp = w.Bp;
     unsigned grid = (unsigned)((B + SWEEP_THREADS - 1) / SWEEP_THREADS);
-    if (ctx->veh.kind == 0) {
-        if (ctx->veh.n_map <= 8) k2_forward<0, 8><<<grid, SWEEP_THREADS, 0, st>>>(s, ctx->veh);
-        else k2_forward<0, 16><<<grid, SWEEP_THREADS, 0, st>>>(s, ctx->veh);
+    if (ctx->sweep_split && !dumps) {  // separate forward / backward kernels (A/B reference for the fused one)
+        SweepArgs s;
+        s.kap = a.kap;
+        s.vacc = reinterpret_cast<double*>(ws + w.vacc_off);
+        s.rot = a.rot; s.len = a.len; s.lap = d_lap;
+        s.vdec = nullptr; s.vmin = nullptr;
+        s.ns = ctx->ns; s.B = B; s.Bp = w.Bp;
+        if (ctx->veh.kind == 0) {
+            if (ctx->veh.n_map <= 8) k2_forward<0, 8><<<grid, SWEEP_THREADS, 0, st>>>(s, ctx->veh);
+            else k2_forward<0, 16><<<grid, SWEEP_THREADS, 0, st>>>(s, ctx->veh);
+        } else {
+            k2_forward<1, 8><<<grid, SWEEP_THREADS, 0, st>>>(s, ctx->veh);
+        }
+        if (ev) LTK_CUDA(ctx, cudaEventRecord(ev[2], st));
+        if (ctx->veh.kind == 0) k3_backward<0><<<grid, SWEEP_THREADS, 0, st>>>(s, ctx->veh);
+        else k3_backward<1><<<grid, SWEEP_THREADS, 0, st>>>(s, ctx->veh);
+        if (ev) LTK_CUDA(ctx, cudaEventRecord(ev[3], st));
+        g_launches.fetch_add(2);
     } else {
-        k2_forward<1, 8><<<grid, SWEEP_THREADS, 0, st>>>(s, ctx->veh);
+        FusedArgs f;
+        f.kap = a.kap;
+        f.stage = reinterpret_cast<double*>(ws + w.vacc_off);
+        f.rot = a.rot; f.len = a.len; f.lap = d_lap;
+        f.vacc_d = dumps ? reinterpret_cast<double*>(ws + w.vaccd_off) : nullptr;
+        f.vdec_d = dumps ? reinterpret_cast<double*>(ws + w.vdec_off) : nullptr;
+        f.vmin_d = dumps ? reinterpret_cast<double*>(ws + w.vmin_off) : nullptr;
+        f.ns = ctx->ns; f.B = B;
+        unsigned gridf = (unsigned)((B + FUSED_THREADS - 1) / FUSED_THREADS);
+        if (ctx->veh.kind == 0) {
+            if (ctx->veh.n_map <= 8) k23_sweep<0, 8><<<gridf, FUSED_THREADS, 0, st>>>(f, ctx->veh);
+            else k23_sweep<0, 16><<<gridf, FUSED_THREADS, 0, st>>>(f, ctx->veh);
+        } else {
+            k23_sweep<1, 8><<<gridf, FUSED_THREADS, 0, st>>>(f, ctx->veh);
+        }
+        if (ev) { LTK_CUDA(ctx, cudaEventRecord(ev[2], st)); LTK_CUDA(ctx, cudaEventRecord(ev[3], st)); }
+        g_launches.fetch_add(1);
     }
-    if (ev) LTK_CUDA(ctx, cudaEventRecord(ev[2], st));
-    if (ctx->veh.kind == 0) k3_backward<0><<<grid, SWEEP_THREADS, 0, st>>>(s, ctx->veh);
-    else k3_backward<1><<<grid, SWEEP_THREADS, 0, st>>>(s, ctx->veh);
-    if (ev) LTK_CUDA(ctx, cudaEventRecord(ev[3], st));
-    g_launches.fetch_add(2);
     LTK_CUDA(ctx, cudaGetLastError());
     return LTK_OK;
 }
@@ -289,6 +309,8 @@ int ltk_create(ltk_ctx** out, int device, const double* h_left_xy, const double*
     ctx->k1_staged_override = -1;
     if (const char* s = getenv("LTK_K1_G")) ctx->k1_g_override = atoi(s);
     if (const char* s = getenv("LTK_K1_STAGED")) ctx->k1_staged_override = atoi(s);
+    ctx->sweep_split = 0;
+    if (const char* s = getenv("LTK_SWEEP")) ctx->sweep_split = (strcmp(s, "split") == 0);
     ctx->k1_threads_override = 0;
     if (const char* s = getenv("LTK_K1_THREADS")) {
         int t = atoi(s);
@@ -431,7 +453,7 @@ int ltk_profile(ltk_ctx* ctx, const double* d_alpha, double* d_s, double* d_k, d
     double* d_lap = reinterpret_cast<double*>(ws + w.total);
     int rc = run_pipeline(ctx, d_alpha, nullptr, 0, 1, d_lap, ws, w, true, st);
     if (rc != LTK_OK) return rc;
-    unrotate_profile<<<8, 256, 0, st>>>(reinterpret_cast<double*>(ws + w.kap_off), reinterpret_cast<double*>(ws + w.vacc_off),
+    unrotate_profile<<<8, 256, 0, st>>>(reinterpret_cast<double*>(ws + w.kap_off), reinterpret_cast<double*>(ws + w.vaccd_off),
                                         reinterpret_cast<double*>(ws + w.vdec_off), reinterpret_cast<double*>(ws + w.vmin_off),
                                         reinterpret_cast<int*>(ws + w.rot_off), reinterpret_cast<double*>(ws + w.len_off),
                                         ctx->ns, w.Bp, ctx->veh.mu_g, d_s, d_k, d_vlocal, d_vacc, d_vdec, d_v);

@@ -101,7 +101,9 @@ class COracle:
         self.N = self.left.shape[1]
         self.veh = vehicle_struct(vehicle)
         self.use_pow = use_pow
-        self.sum_mode = 1 if device_sum_order else 0
+        # True / "fused": summation order of the fused sweep kernel (the default device path);
+        # "split": order of the separate backward kernel (LTK_SWEEP=split)
+        self.sum_mode = {False: 0, None: 0, True: 2, "fused": 2, "split": 1}[device_sum_order]
 
     def _modes(self):
         L = lib()

@@ -46,8 +46,12 @@ typedef struct {
 /* 1: square with libm pow(x, 2.0) exactly like CPython / numpy scalars do (bit-identical to the
  * reference on the same libm); 0: x*x (what the CUDA kernels do). Differs in ~0.08 % of calls by 1 ulp. */
 static int g_use_pow = 0;
-/* 0: numpy pairwise order for the lap sum (what the reference does); 1: the CUDA K3 kernel's order
- * (sequential from sample p-1 downwards, wrapping, sample p last) -- for bit-for-bit device checks. */
+/* 0: numpy pairwise order for the lap sum (what the reference does);
+ * 1: the order of the CUDA K3 kernel (sequential from sample p-1 downwards, wrapping, sample p last);
+ * 2: the order of the fused CUDA sweep kernel K23: with rows r = (q - p) mod n, h = (n-1)/2 rounded down,
+ *    lap_f = rows n-h .. n-1 ascending, lap_b = rows h .. 1 descending,
+ *    lap = ((lap_f + lap_b) [+ middle row h+1 when n-1 is odd]) + row 0.
+ * 1 and 2 exist for bit-for-bit checks of the device kernels. */
 static int g_sum_mode = 0;
 void lto_set_sum_mode(int m) { g_sum_mode = m; }
 static volatile double g_two = 2.0; /* volatile: stops gcc folding pow(x, 2.0) into x*x */
@@ -150,6 +154,17 @@ static double sweeps_one(const lto_vehicle *veh, const double *k, int ns, double
     }
     if (o_vacc) memcpy(o_vacc, va, sizeof(double) * n);
     if (o_vdec) memcpy(o_vdec, vd, sizeof(double) * n);
+    if (g_sum_mode == 2) {
+        int rows = n - 1, h = rows / 2, has_mid = rows & 1;
+        double lap_f = 0.0, lap_b = 0.0;
+#define ROWQ(r) (((p + (r)) >= n) ? (p + (r)) - n : (p + (r)))
+        for (int r = n - h; r <= n - 1; ++r) lap_f = lap_f + term[ROWQ(r)];
+        for (int r = h; r >= 1; --r) lap_b = lap_b + term[ROWQ(r)];
+        double lap = lap_f + lap_b;
+        if (has_mid) lap = lap + term[ROWQ(h + 1)];
+#undef ROWQ
+        return lap + term[p];
+    }
     if (g_sum_mode == 1) {
         double lap = 0.0;
         for (int i = 1; i < n; ++i) {
