@@ -70,7 +70,8 @@ VehDev make_vehdev(const ltk_vehicle& v)
     d.kind = v.kind;
     d.n_map = v.n_map;
     d.mass = v.mass;
-    d.inv_mass = 1.0 / v.mass;  // correctly rounded; see div_by_const
+    d.half_mass = 0.5 * v.mass;           // exact
+    d.inv_half_mass = 1.0 / d.half_mass;  // correctly rounded; see div_by_const / forward_step
     d.mu_g = v.mu_g;
     d.f_max = v.f_max;
     d.f_max_sq = v.f_max_sq;

@@ -54,9 +54,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, 8) k23_sweep(FusedArgs a, VehDe
     const double L = a.len[b];
     const double step = L / (double)(a.ns - 1);
     GridClock cf, cb;  // forward / backward position on the np.linspace grid
-    cf.L = cb.L = L; cf.step = cb.step = step; cf.nd = cb.nd = (double)n;
-    cf.kd = (double)p; cf.s_k = cf.kd * step;
-    if (p == 0) { cb.kd = cb.nd - 1.0; cb.s_k = L; } else { cb.kd = (double)(p - 1); cb.s_k = (double)p * step; }
+    cf.L = cb.L = L; cf.step = cb.step = step; cf.n = cb.n = n;
+    cf.k = p; cf.s_k = (double)p * step;
+    if (p == 0) { cb.k = n - 1; cb.s_k = L; } else { cb.k = p - 1; cb.s_k = (double)p * step; }
 
     // row 0 = the slowest sample: both chains start from v_local there (velocity.py:34-36, :58-61)
     const double k0 = a.kap[base];
@@ -217,8 +217,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 8) k23_sweep(FusedArgs a, VehDe
                     ds_f = cf.advance();
                     double ds_b = cb.retreat();
                     double vd = backward_step<KIND, false>(V, vb, kb, vlb[u], ds_b);
-                    double v1 = (va < fo[u]) ? va : fo[u];  // velocity.py:26
-                    double v2 = (bo[u] < vd) ? bo[u] : vd;
+                    double v1 = lt_nonneg<false>(va, fo[u]) ? va : fo[u];  // velocity.py:26
+                    double v2 = lt_nonneg<false>(bo[u], vd) ? bo[u] : vd;
                     lap_f = lap_f + ddiv<false>(ds_f, v1);  // tbn.py:53
                     lap_b = lap_b + ddiv<false>(ds_b, v2);
                     vf = va; kf = fc[u];
