@@ -176,7 +176,18 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout; keep stdout for the one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     tj, vj = data_paths(args.vehicle)
     track = ltk.Track(tj, track_width=WIDTH, quiet=True)
     ev = ltk.LapTimeEvaluator(track, ltk.load_vehicle(vj), "bayes", args.ns, device=local)

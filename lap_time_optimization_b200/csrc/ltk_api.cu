@@ -145,7 +145,7 @@ int k1a_threads(const ltk_ctx* ctx);
 
 bool pick_k1(const ltk_ctx* ctx, K1Config* out)
 {
-    const int cand_g[2] = {16, 8};
+    const int cand_g[2] = {8, 16};  // measured: two co-resident half-tile CTAs per SM beat one full-tile CTA
     for (int staged = 1; staged >= 0; --staged) {
         if (ctx->k1_staged_override >= 0 && staged != ctx->k1_staged_override) continue;
         for (int gi = 0; gi < 2; ++gi) {
