@@ -21,6 +21,7 @@ struct ltk_ctx {
     double* d_diff;  // [2][N]
     VehDev veh;
     // scratch owned by the context
+    int4* d_lut;  // engine cell table of the fused sweep (nullptr: none)
     double* d_topk_lap;
     long long* d_topk_idx;
     void* d_profile_ws;
@@ -90,7 +91,74 @@ VehDev make_vehdev(const ltk_vehicle& v)
         }
         d.ext_b[n] = v.map_v[n - 1]; d.ext_f[n] = v.map_f[n - 1]; d.ext_s[n] = 0.0;
     }
+    // curvature window of the regular path: 2^-511 <= k < 2^513 ...
+    d.k_lo_hi = 0x20000000;
+    d.k_span_hi = 0x40000000u;
+    bool engine_nonneg = true;
+    if (v.kind == 0) {
+        for (int i = 0; i < v.n_map; ++i) engine_nonneg = engine_nonneg && (v.map_f[i] >= 0.0);
+    } else if (v.cr2 > 0.0) {
+        // ... and, for the polynomial engine e0 - cr2 v^2, k large enough that v^2 <= mu g / k keeps it >= 0
+        if (v.e0 > 0.0 && v.mu_g > 0.0) {
+            double k_min = v.mu_g * v.cr2 / (0.99 * v.e0);
+            int hi;
+            long long bits;
+            memcpy(&bits, &k_min, sizeof(bits));
+            hi = (int)(bits >> 32) + 1;  // round the window's lower end up
+            if (hi > d.k_lo_hi) {
+                unsigned top = (unsigned)d.k_lo_hi + d.k_span_hi;
+                d.k_span_hi = ((unsigned)hi < top) ? top - (unsigned)hi : 0u;
+                d.k_lo_hi = hi;
+            }
+        } else {
+            engine_nonneg = false;
+        }
+    } else {
+        engine_nonneg = (v.e0 >= 0.0);
+    }
+    if (!engine_nonneg) d.k_span_hi = 0u;  // never take the regular path (it assumes accel >= 0)
+    d.lut_shift = 0; d.lut_base = 0; d.lut_top = -1;
     return d;
+}
+
+// Engine cell table (EngineLut in ltk_sweep_fused.cuh).  Picks the coarsest split of the high word that
+// leaves at most one map node per cell; returns the number of cells (0: no table fits).
+int build_engine_lut(const ltk_vehicle& v, VehDev* d, int4* cells)
+{
+    if (v.kind != 0) return 0;
+    const int n = v.n_map;
+    int hi[LTK_MAX_ENGINE_MAP];
+    long long bits[LTK_MAX_ENGINE_MAP];
+    for (int i = 0; i < n; ++i) {
+        memcpy(&bits[i], &v.map_v[i], sizeof(double));
+        hi[i] = (int)(bits[i] >> 32);
+    }
+    for (int shift = 20; shift >= 0; --shift) {
+        bool distinct = true;
+        for (int i = 1; i < n && distinct; ++i) distinct = (hi[i] >> shift) != (hi[i - 1] >> shift);
+        if (!distinct) continue;
+        const int first = hi[0] >> shift, last = hi[n - 1] >> shift;
+        const long long ncell = (long long)last - first + 3;  // one catch-all cell on either side
+        if (ncell > LTK_LUT_MAX_CELLS) return 0;              // finer shifts only need more cells
+        const int base = first - 1;
+        const long long never = 0x7fffffffffffffffLL;
+        int node = 0;  // nodes below the current cell
+        for (int c = 0; c < (int)ncell; ++c) {
+            const int cell_id = base + c;
+            long long thr = never;
+            if (node < n && (hi[node] >> shift) == cell_id && c > 0 && c < (int)ncell - 1) thr = bits[node];
+            cells[c].x = (int)(unsigned)(thr & 0xffffffffLL);
+            cells[c].y = (int)(thr >> 32);
+            cells[c].z = node;
+            cells[c].w = 0;
+            if (thr != never) ++node;
+        }
+        d->lut_shift = shift;
+        d->lut_base = base;
+        d->lut_top = (int)ncell - 1;
+        return (int)ncell;
+    }
+    return 0;
 }
 
 int check_vehicle(const ltk_vehicle* v)
@@ -250,6 +318,7 @@ int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m
         g_launches.fetch_add(2);
     } else {
         FusedArgs f;
+        f.lut = ctx->d_lut; f.Bp = w.Bp;
         f.kap = a.kap;
         f.stage = reinterpret_cast<double*>(ws + w.vacc_off);
         f.rot = a.rot; f.len = a.len; f.lap = d_lap;
@@ -257,9 +326,10 @@ int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m
         f.vdec_d = dumps ? reinterpret_cast<double*>(ws + w.vdec_off) : nullptr;
         f.vmin_d = dumps ? reinterpret_cast<double*>(ws + w.vmin_off) : nullptr;
         f.ns = ctx->ns; f.B = B;
-        unsigned gridf = (unsigned)((B + FUSED_THREADS - 1) / FUSED_THREADS);
+        unsigned gridf = (unsigned)((w.Bp + FUSED_THREADS - 1) / FUSED_THREADS);
         if (ctx->veh.kind == 0) {
-            if (ctx->veh.n_map <= 8) k23_sweep<0, 8><<<gridf, FUSED_THREADS, 0, st>>>(f, ctx->veh);
+            if (ctx->veh.lut_top >= 0) k23_sweep<0, 0><<<gridf, FUSED_THREADS, 0, st>>>(f, ctx->veh);
+            else if (ctx->veh.n_map <= 8) k23_sweep<0, 8><<<gridf, FUSED_THREADS, 0, st>>>(f, ctx->veh);
             else k23_sweep<0, 16><<<gridf, FUSED_THREADS, 0, st>>>(f, ctx->veh);
         } else {
             k23_sweep<1, 8><<<gridf, FUSED_THREADS, 0, st>>>(f, ctx->veh);
@@ -317,6 +387,16 @@ int ltk_create(ltk_ctx** out, int device, const double* h_left_xy, const double*
         int t = atoi(s);
         if (t == 256 || t == 512 || t == 1024) ctx->k1_threads_override = t;
     }
+    int4 lut_cells[LTK_LUT_MAX_CELLS];
+    const int n_cells = getenv("LTK_NO_ENGINE_LUT") ? 0 : build_engine_lut(*vehicle, &ctx->veh, lut_cells);
+    if (n_cells > 0) {
+        if ((e = cudaMalloc(&ctx->d_lut, sizeof(int4) * n_cells)) != cudaSuccess ||
+            (e = cudaMemcpy(ctx->d_lut, lut_cells, sizeof(int4) * n_cells, cudaMemcpyHostToDevice)) != cudaSuccess) {
+            fail(nullptr, LTK_E_CUDA, "engine table allocation", e);
+            ltk_destroy(ctx);
+            return LTK_E_CUDA;
+        }
+    }
     size_t bytes = sizeof(double) * 2 * (size_t)n_ctrl;
     if ((e = cudaMalloc(&ctx->d_left, bytes)) != cudaSuccess || (e = cudaMalloc(&ctx->d_diff, bytes)) != cudaSuccess ||
         (e = cudaMalloc(&ctx->d_topk_lap, sizeof(double) * TOPK_MAX_BLOCKS * TOPK_MAX)) != cudaSuccess ||
@@ -343,6 +423,7 @@ void ltk_destroy(ltk_ctx* ctx)
     DeviceGuard guard(ctx->device);
     cudaFree(ctx->d_left);
     cudaFree(ctx->d_diff);
+    cudaFree(ctx->d_lut);
     cudaFree(ctx->d_topk_lap);
     cudaFree(ctx->d_topk_idx);
     cudaFree(ctx->d_profile_ws);

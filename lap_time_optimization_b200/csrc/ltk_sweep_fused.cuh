@@ -14,12 +14,27 @@
 //
 // HBM traffic is exactly that of the separate kernels: every curvature row read twice, every staged
 // value written once and read once.
+//
+// The kernel is bound by the FP64 pipe (and by issue slots next to it), so the regular path is written
+// to issue as few instructions as the reference's arithmetic allows without changing a single bit:
+//   * min before sqrt.  velocity.py:44-50 computes  v = v_local  if v_local <= v_prev  else
+//     min(v_local, sqrt(v_prev^2 + 2 a ds)),  v_local = sqrt(mu g / k).  With a >= 0 this equals
+//     sqrt(min(mu g / k, v_prev^2 + 2 a ds)) bit for bit: correctly rounded sqrt is monotone, so
+//     min(sqrt x, sqrt y) = sqrt(min(x, y)); and when v_local <= v_prev the squared limit
+//     w = RN(v_prev^2 + ..) >= RN(v_local^2) gives sqrt(min(.)) in [sqrt(RN(v_local^2)), v_local] =
+//     {v_local}.  One square root and one comparison per step disappear.  (a >= 0: traction is >= 0 by
+//     construction; the engine force is >= 0 on the regular path, see VehDev::k_lo_hi.)
+//   * engine map through a cell table indexed by the leading bits of v (EngineLut) instead of one
+//     comparison per node.
+//   * the np.linspace clock: the wrap-around of the sample index happens once per chain and lane, so
+//     blocks in which no lane of the warp wraps run a select-free clock (warp vote).
 #pragma once
 
 namespace ltk {
 
 constexpr int FUSED_THREADS = 64;
 constexpr int FUSED_UNROLL = 4;
+constexpr unsigned FULL_MASK = 0xffffffffu;
 
 struct FusedArgs {
     const double* kap;  // [n][tile-blocked] rotated curvature
@@ -30,42 +45,202 @@ struct FusedArgs {
     double* vacc_d;     // optional dumps, [n][tile-blocked]
     double* vdec_d;
     double* vmin_d;
+    const int4* lut;    // engine cell table (EngineLut), device memory; nullptr when ENG != 0
     int ns;
-    long long B;
+    long long B, Bp;
 };
 
-template <int KIND, int NPAD>
+// ---- engine map by cell table ---------------------------------------------------------------------
+// Cell c = clamp((hi32(v) >> shift) - base, 0, cells-1) holds at most one node of the map: record
+// (thr.lo, thr.hi, j0, -) with j = j0 + (bits(v) >= thr) = #{m : v >= map_v[m]}  (np.interp's segment,
+// vehicle.py:25-27).  Cell 0 collects everything below the first node's cell, the last cell everything
+// above the last node's cell.  Integer comparisons on the bit patterns are exact for v >= 0.
+struct __align__(16) EngineSeg {
+    double s, b, f, pad;  // slope, left abscissa, left ordinate of extended segment j (see VehDev)
+};
+struct FusedShared {
+    EngineSeg seg[LTK_MAX_ENGINE_MAP + 1];
+    int4 cell[LTK_LUT_MAX_CELLS];
+};
+
+template <int ENG>
+__device__ __forceinline__ double engine_fast(const VehDev& V, const FusedShared& S, double x)
+{
+    int j;
+    if (ENG == 0) {
+        int c = (__double2hiint(x) >> V.lut_shift) - V.lut_base;
+        c = max(c, 0);
+        c = min(c, V.lut_top);
+        const int4 r = S.cell[c];
+        const long long thr = (long long)(((unsigned long long)(unsigned)r.y << 32) | (unsigned)r.x);
+        j = r.z + ((__double_as_longlong(x) >= thr) ? 1 : 0);
+    } else {
+        const long long xi = __double_as_longlong(x);
+        j = 0;
+#pragma unroll
+        for (int m = 0; m < ENG; ++m) j += (xi >= V.thr[m]) ? 1 : 0;
+    }
+    const EngineSeg g = S.seg[j];
+    return g.s * (x - g.b) + g.f;
+}
+
+// curvature usable by the unguarded sequences AND small enough a local limit that the engine force
+// stays non-negative (VehDev::k_lo_hi / k_span_hi are chosen on the host)
+__device__ __forceinline__ bool kappa_regular(const VehDev& V, double k)
+{
+    return (unsigned)(__double2hiint(k) - V.k_lo_hi) < V.k_span_hi;
+}
+
+// velocity.py:44-50 as sqrt(min(.)) -- see the header comment.  wl = mu g / k of the row being entered.
+template <int KIND, int ENG>
+__device__ __forceinline__ double forward_fast(const VehDev& V, const FusedShared& S, double v_prev,
+                                               double k_prev, double wl, double ds)
+{
+    double w = v_prev * v_prev;
+    double tr = traction_from<false>(V, lateral_force<KIND>(V, v_prev, w, k_prev));
+    double en = (KIND == 0) ? engine_fast<ENG>(V, S, v_prev) : V.e0 - V.cr2 * w;
+    double force = (en < tr) ? en : tr;
+    double accel2 = div_by_const<false>(force, V.half_mass, V.inv_half_mass);
+    double wlim = w + accel2 * ds;
+    return dsqrt<false>((wlim < wl) ? wlim : wl);
+}
+
+// velocity.py:68-73, same transformation
+template <int KIND>
+__device__ __forceinline__ double backward_fast(const VehDev& V, double v_next, double k_next, double wl, double ds)
+{
+    double w = v_next * v_next;
+    double tr = traction_from<false>(V, lateral_force<KIND>(V, v_next, w, k_next));
+    double decel2 = div_by_const<false>(tr, V.half_mass, V.inv_half_mass);
+    double wlim = w + decel2 * ds;
+    return dsqrt<false>((wlim < wl) ? wlim : wl);
+}
+
+// state of the two chains of one candidate
+struct Chains {
+    double vf, kf, vb, kb;  // velocity and curvature of the row each chain just left
+    double ds_f;            // np.diff(s) of the interval the forward chain crosses next
+    double lap_f, lap_b;
+    int qf, qb;             // clocks: see GridClock (forward: current sample; backward: interval to enter)
+    double sf, sb;
+    double step, L;
+    int n;
+};
+
+template <bool WRAP>
+__device__ __forceinline__ double clock_advance(Chains& c)
+{
+    int k1 = c.qf + 1;
+    double s1 = (double)k1 * c.step;
+    if (WRAP) {
+        bool wrap = (k1 == c.n);
+        s1 = wrap ? c.L : s1;
+        double ds = s1 - c.sf;
+        c.qf = wrap ? 0 : k1;
+        c.sf = wrap ? 0.0 : s1;
+        return ds;
+    }
+    double ds = s1 - c.sf;
+    c.qf = k1;
+    c.sf = s1;
+    return ds;
+}
+template <bool WRAP>
+__device__ __forceinline__ double clock_retreat(Chains& c)
+{
+    double s_lo = (double)c.qb * c.step;
+    double ds = c.sb - s_lo;
+    if (WRAP) {
+        bool wrap = (c.qb == 0);
+        c.sb = wrap ? c.L : s_lo;
+        c.qb = wrap ? c.n - 1 : c.qb - 1;
+        return ds;
+    }
+    c.sb = s_lo;
+    c.qb = c.qb - 1;
+    return ds;
+}
+
+// U row pairs on the regular path.  PHASE 1 parks, PHASE 2 meets the parked values and accumulates.
+template <int KIND, int ENG, int PHASE, bool WRAP>
+__device__ __forceinline__ void fused_block(const VehDev& V, const FusedShared& S, Chains& c,
+                                            const double (&fc)[FUSED_UNROLL], const double (&bc)[FUSED_UNROLL],
+                                            const double (&fo)[FUSED_UNROLL], const double (&bo)[FUSED_UNROLL],
+                                            double* sfp, double* sbp)
+{
+    constexpr int U = FUSED_UNROLL;
+    constexpr size_t P = TILE;
+    double wlf[U], wlb[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {  // independent of the recurrences: issued ahead of them
+        wlf[u] = ddiv<false>(V.mu_g, fc[u]);
+        wlb[u] = ddiv<false>(V.mu_g, bc[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        double va = forward_fast<KIND, ENG>(V, S, c.vf, c.kf, wlf[u], c.ds_f);
+        c.ds_f = clock_advance<WRAP>(c);
+        double ds_b = clock_retreat<WRAP>(c);
+        double vd = backward_fast<KIND>(V, c.vb, c.kb, wlb[u], ds_b);
+        if (PHASE == 1) {
+            sfp[(size_t)u * P] = va;
+            *(sbp - (size_t)u * P) = vd;
+        } else {
+            double v1 = (va < fo[u]) ? va : fo[u];  // velocity.py:26
+            double v2 = (bo[u] < vd) ? bo[u] : vd;
+            c.lap_f = c.lap_f + ddiv<false>(c.ds_f, v1);  // tbn.py:53
+            c.lap_b = c.lap_b + ddiv<false>(ds_b, v2);
+        }
+        c.vf = va; c.kf = fc[u];
+        c.vb = vd; c.kb = bc[u];
+    }
+}
+
+template <int KIND, int ENG>
 __global__ void __launch_bounds__(FUSED_THREADS, 8) k23_sweep(FusedArgs a, VehDev V)
 {
     constexpr int U = FUSED_UNROLL;
     constexpr size_t P = TILE;  // row pitch in doubles
-    __shared__ EngineTable T;
+    constexpr int NPAD = (ENG == 16) ? 16 : 8;  // comparison count of the library-operator path
+    __shared__ FusedShared S;
+    __shared__ EngineTable T;  // library-operator path (tails, irregular blocks, dumps)
     if (KIND == 0) {
         load_engine_table(T, V, threadIdx.x, FUSED_THREADS);
+        for (int i = threadIdx.x; i <= LTK_MAX_ENGINE_MAP; i += FUSED_THREADS) {
+            S.seg[i].s = V.ext_s[i]; S.seg[i].b = V.ext_b[i]; S.seg[i].f = V.ext_f[i]; S.seg[i].pad = 0.0;
+        }
+        if (ENG == 0)
+            for (int i = threadIdx.x; i <= V.lut_top; i += FUSED_THREADS) S.cell[i] = a.lut[i];
         __syncthreads();
     }
-    const long long b = (long long)blockIdx.x * FUSED_THREADS + threadIdx.x;
-    if (b >= a.B) return;
+    const long long b_raw = (long long)blockIdx.x * FUSED_THREADS + threadIdx.x;
+    if (b_raw - (threadIdx.x & 31) >= a.Bp) return;  // whole warp beyond the padded population
+    // lanes in [B, Bp) sweep the padding copies K1 wrote (so that warp votes see a full warp)
+    const long long b = b_raw;
     const int n = a.ns - 1;
     const size_t base = tile_base(b, n);
     const int p = a.rot[b];
     const bool dump = a.vdec_d != nullptr;
 
-    const double L = a.len[b];
-    const double step = L / (double)(a.ns - 1);
+    Chains c;
+    c.L = a.len[b];
+    c.step = c.L / (double)(a.ns - 1);
+    c.n = n;
     GridClock cf, cb;  // forward / backward position on the np.linspace grid
-    cf.L = cb.L = L; cf.step = cb.step = step; cf.n = cb.n = n;
-    cf.k = p; cf.s_k = (double)p * step;
-    if (p == 0) { cb.k = n - 1; cb.s_k = L; } else { cb.k = p - 1; cb.s_k = (double)p * step; }
+    cf.L = cb.L = c.L; cf.step = cb.step = c.step; cf.n = cb.n = n;
+    cf.k = p; cf.s_k = (double)p * c.step;
+    if (p == 0) { cb.k = n - 1; cb.s_k = c.L; } else { cb.k = p - 1; cb.s_k = (double)p * c.step; }
 
     // row 0 = the slowest sample: both chains start from v_local there (velocity.py:34-36, :58-61)
     const double k0 = a.kap[base];
     const double v0 = sqrt(V.mu_g / k0);
-    double vf = v0, kf = k0;  // forward state: v_acc and curvature of the row just left
-    double vb = v0, kb = k0;  // backward state
-    double ds_f = cf.advance();  // np.diff(s) of the interval the forward chain crosses next
-    const double term0 = ds_f / v0;
+    c.vf = v0; c.kf = k0;
+    c.vb = v0; c.kb = k0;
+    c.ds_f = cf.advance();
+    const double term0 = c.ds_f / v0;
     if (dump) { a.vacc_d[base] = v0; a.vdec_d[base] = v0; a.vmin_d[base] = v0; }
+    c.qf = cf.k; c.sf = cf.s_k; c.qb = cb.k; c.sb = cb.s_k;
+    c.lap_f = 0.0; c.lap_b = 0.0;
 
     const int rows = n - 1;           // rows 1 .. n-1
     const int h = rows / 2;           // steps per phase
@@ -77,44 +252,39 @@ __global__ void __launch_bounds__(FUSED_THREADS, 8) k23_sweep(FusedArgs a, VehDe
     double* sbp = a.stage + base + (size_t)(n - 1) * P;
     size_t rf = base + P, rb = base + (size_t)(n - 1) * P;     // same cursors as offsets (dumps)
 
-    double lap_f = 0.0, lap_b = 0.0;
-
-    // ---- generic single step (library operators); used for tails, the middle row, irregular blocks ----
-    auto step_safe = [&](bool do_f, bool do_b, int phase) {
-        double va = 0.0, vd = 0.0;
-        if (do_f) {
+    // ---- generic single step (library operators, reference branch structure); used for tails, the
+    //      middle row, irregular blocks and dumps ----------------------------------------------------
+    auto step_safe = [&](int phase) {
+        double va, vd;
+        {
             double kc = *kfp;
-            va = forward_step<KIND, NPAD, true>(V, T, vf, kf, local_limit<true>(V, kc), ds_f);
-            vf = va; kf = kc;
-            ds_f = cf.advance();
+            va = forward_step<KIND, NPAD, true>(V, T, c.vf, c.kf, local_limit<true>(V, kc), c.ds_f);
+            c.vf = va; c.kf = kc;
+            c.ds_f = clock_advance<true>(c);
         }
-        double ds_b = 0.0;
-        if (do_b) {
+        double ds_b;
+        {
             double kc = *kbp;
-            ds_b = cb.retreat();
-            vd = backward_step<KIND, true>(V, vb, kb, local_limit<true>(V, kc), ds_b);
-            vb = vd; kb = kc;
+            ds_b = clock_retreat<true>(c);
+            vd = backward_step<KIND, true>(V, c.vb, c.kb, local_limit<true>(V, kc), ds_b);
+            c.vb = vd; c.kb = kc;
         }
         if (phase == 1) {
-            if (do_f) *sfp = va;
-            if (do_b) *sbp = vd;
-            if (dump) { if (do_f) a.vacc_d[rf] = va; if (do_b) a.vdec_d[rb] = vd; }
-        } else if (phase == 2) {
-            if (do_f) {
-                double o = *sfp;  // v_dec parked by the backward chain
-                double v = (va < o) ? va : o;
-                lap_f = lap_f + ds_f / v;
-                if (dump) { a.vacc_d[rf] = va; a.vmin_d[rf] = v; }
-            }
-            if (do_b) {
-                double o = *sbp;  // v_acc parked by the forward chain
-                double v = (o < vd) ? o : vd;
-                lap_b = lap_b + ds_b / v;
-                if (dump) { a.vdec_d[rb] = vd; a.vmin_d[rb] = v; }
-            }
+            *sfp = va;
+            *sbp = vd;
+            if (dump) { a.vacc_d[rf] = va; a.vdec_d[rb] = vd; }
+        } else {
+            double o = *sfp;  // v_dec parked by the backward chain
+            double v = (va < o) ? va : o;
+            c.lap_f = c.lap_f + c.ds_f / v;
+            if (dump) { a.vacc_d[rf] = va; a.vmin_d[rf] = v; }
+            o = *sbp;  // v_acc parked by the forward chain
+            v = (o < vd) ? o : vd;
+            c.lap_b = c.lap_b + ds_b / v;
+            if (dump) { a.vdec_d[rb] = vd; a.vmin_d[rb] = v; }
         }
-        if (do_f) { kfp += P; sfp += P; rf += P; }
-        if (do_b) { kbp -= P; sbp -= P; rb -= P; }
+        kfp += P; sfp += P; rf += P;
+        kbp -= P; sbp -= P; rb -= P;
     };
 
     // ---- phase 1 -----------------------------------------------------------------------------------
@@ -134,50 +304,40 @@ __global__ void __launch_bounds__(FUSED_THREADS, 8) k23_sweep(FusedArgs a, VehDe
                 fn[u] = in ? kfp[(size_t)(U + u) * P] : 1.0;
                 bn[u] = in ? *(kbp - (size_t)(U + u) * P) : 1.0;
             }
-            bool regular = is_regular(vf) && is_regular(kf) && is_regular(vb) && is_regular(kb);
+            bool regular = is_regular(c.vf) && kappa_regular(V, c.kf) && is_regular(c.vb) && kappa_regular(V, c.kb);
 #pragma unroll
-            for (int u = 0; u < U; ++u) regular = regular && is_regular(fc[u]) && is_regular(bc[u]);
-            if (regular) {
-                double vlf[U], vlb[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) { vlf[u] = local_limit<false>(V, fc[u]); vlb[u] = local_limit<false>(V, bc[u]); }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    double va = forward_step<KIND, NPAD, false>(V, T, vf, kf, vlf[u], ds_f);
-                    ds_f = cf.advance();
-                    double ds_b = cb.retreat();
-                    double vd = backward_step<KIND, false>(V, vb, kb, vlb[u], ds_b);
-                    sfp[(size_t)u * P] = va;
-                    *(sbp - (size_t)u * P) = vd;
-                    vf = va; kf = fc[u];
-                    vb = vd; kb = bc[u];
-                }
+            for (int u = 0; u < U; ++u) regular = regular && kappa_regular(V, fc[u]) && kappa_regular(V, bc[u]);
+            const bool nowrap = (c.qf + U < n) && (c.qb >= U);
+            const bool all_regular = __all_sync(FULL_MASK, regular);
+            if (all_regular) {
+                if (__all_sync(FULL_MASK, nowrap)) fused_block<KIND, ENG, 1, false>(V, S, c, fc, bc, fc, bc, sfp, sbp);
+                else fused_block<KIND, ENG, 1, true>(V, S, c, fc, bc, fc, bc, sfp, sbp);
                 kfp += (size_t)U * P; sfp += (size_t)U * P; rf += (size_t)U * P;
                 kbp -= (size_t)U * P; sbp -= (size_t)U * P; rb -= (size_t)U * P;
-            } else {
+            } else {  // zero / inf / nan curvature somewhere in this block of this warp
 #pragma unroll 1
-                for (int u = 0; u < U; ++u) step_safe(true, true, 1);
+                for (int u = 0; u < U; ++u) step_safe(1);
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) { fc[u] = fn[u]; bc[u] = bn[u]; }
         }
     }
 #pragma unroll 1
-    for (; t < h; ++t) step_safe(true, true, 1);
+    for (; t < h; ++t) step_safe(1);
 
     // ---- middle row (odd row count): both chains arrive at row h+1 ------------------------------------
     double term_mid = 0.0;
     if (has_mid) {
         double kc = *kfp;
         double vl = local_limit<true>(V, kc);
-        double va = forward_step<KIND, NPAD, true>(V, T, vf, kf, vl, ds_f);
-        ds_f = cf.advance();
-        double ds_b = cb.retreat();
-        double vd = backward_step<KIND, true>(V, vb, kb, vl, ds_b);
+        double va = forward_step<KIND, NPAD, true>(V, T, c.vf, c.kf, vl, c.ds_f);
+        c.ds_f = clock_advance<true>(c);
+        double ds_b = clock_retreat<true>(c);
+        double vd = backward_step<KIND, true>(V, c.vb, c.kb, vl, ds_b);
         double v = (va < vd) ? va : vd;
         term_mid = ds_b / v;
         if (dump) { a.vacc_d[rf] = va; a.vdec_d[rf] = vd; a.vmin_d[rf] = v; }
-        vf = va; kf = kc; vb = vd; kb = kc;
+        c.vf = va; c.kf = kc; c.vb = vd; c.kb = kc;
         kfp += P; sfp += P; rf += P;
         kbp -= P; sbp -= P; rb -= P;
     }
@@ -203,43 +363,31 @@ __global__ void __launch_bounds__(FUSED_THREADS, 8) k23_sweep(FusedArgs a, VehDe
                 bn[u] = in ? *(kbp - (size_t)(U + u) * P) : 1.0;
                 bon[u] = in ? *(sbp - (size_t)(U + u) * P) : 1.0;
             }
-            bool regular = is_regular(vf) && is_regular(kf) && is_regular(vb) && is_regular(kb);
+            bool regular = is_regular(c.vf) && kappa_regular(V, c.kf) && is_regular(c.vb) && kappa_regular(V, c.kb);
 #pragma unroll
             for (int u = 0; u < U; ++u)
-                regular = regular && is_regular(fc[u]) && is_regular(bc[u]) && is_regular(fo[u]) && is_regular(bo[u]);
-            if (regular) {
-                double vlf[U], vlb[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) { vlf[u] = local_limit<false>(V, fc[u]); vlb[u] = local_limit<false>(V, bc[u]); }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    double va = forward_step<KIND, NPAD, false>(V, T, vf, kf, vlf[u], ds_f);
-                    ds_f = cf.advance();
-                    double ds_b = cb.retreat();
-                    double vd = backward_step<KIND, false>(V, vb, kb, vlb[u], ds_b);
-                    double v1 = lt_nonneg<false>(va, fo[u]) ? va : fo[u];  // velocity.py:26
-                    double v2 = lt_nonneg<false>(bo[u], vd) ? bo[u] : vd;
-                    lap_f = lap_f + ddiv<false>(ds_f, v1);  // tbn.py:53
-                    lap_b = lap_b + ddiv<false>(ds_b, v2);
-                    vf = va; kf = fc[u];
-                    vb = vd; kb = bc[u];
-                }
+                regular = regular && kappa_regular(V, fc[u]) && kappa_regular(V, bc[u]) && is_regular(fo[u]) && is_regular(bo[u]);
+            const bool nowrap = (c.qf + U < n) && (c.qb >= U);
+            const bool all_regular = __all_sync(FULL_MASK, regular);
+            if (all_regular) {
+                if (__all_sync(FULL_MASK, nowrap)) fused_block<KIND, ENG, 2, false>(V, S, c, fc, bc, fo, bo, sfp, sbp);
+                else fused_block<KIND, ENG, 2, true>(V, S, c, fc, bc, fo, bo, sfp, sbp);
                 kfp += (size_t)U * P; sfp += (size_t)U * P; rf += (size_t)U * P;
                 kbp -= (size_t)U * P; sbp -= (size_t)U * P; rb -= (size_t)U * P;
-            } else {
+            } else {  // zero / inf / nan curvature somewhere in this block of this warp
 #pragma unroll 1
-                for (int u = 0; u < U; ++u) step_safe(true, true, 2);
+                for (int u = 0; u < U; ++u) step_safe(2);
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) { fc[u] = fn[u]; bc[u] = bn[u]; fo[u] = fon[u]; bo[u] = bon[u]; }
         }
     }
 #pragma unroll 1
-    for (; t < h; ++t) step_safe(true, true, 2);
+    for (; t < h; ++t) step_safe(2);
 
-    double lap = lap_f + lap_b;
+    double lap = c.lap_f + c.lap_b;
     if (has_mid) lap = lap + term_mid;
-    a.lap[b] = lap + term0;
+    if (b < a.B) a.lap[b] = lap + term0;
 }
 
 }  // namespace ltk
