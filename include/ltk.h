@@ -78,12 +78,14 @@ int ltk_workspace_bytes(const ltk_ctx *ctx, int64_t B, size_t *out_bytes);
  * (trajectory.py:40-58): Track.control_points* (track.py:82-94), Path.__init__ (path.py:20-26),
  * np.linspace sampling, Path.curvature (path.py:36-61), VelocityProfile (velocity.py:14-76),
  * Vehicle.engine_force/traction (vehicle.py:25-35, vehicleMX5.py:19-37), lap_time (:51-54).
- * Kernels launched: K1 spline+curvature, K2 forward sweep, K3 backward sweep + lap reduction. */
+ * Kernels launched: K1a spline solve, K1b curvature (rotated write-out), K23 forward + backward sweeps
+ * with the lap-time sum. */
 int ltk_eval_alphas(ltk_ctx *ctx, const double *d_alphas, int64_t B, double *d_lap,
                     void *d_workspace, size_t workspace_bytes, void *stream);
 
-/* Measurement hook: same work as ltk_eval_alphas, with CUDA events recorded on `stream` around each of
- * the three kernels; synchronises and writes their durations in milliseconds to h_ms[3] = {K1, K2, K3}. */
+/* Measurement hook: same work as ltk_eval_alphas, with CUDA events recorded on `stream` around each
+ * kernel; synchronises and writes the durations in milliseconds to h_ms[4] = {K1a, K1b, K23, -1}
+ * ({K1a, K1b, K2, K3} when the sweeps run as two kernels, LTK_SWEEP=split). */
 int ltk_eval_alphas_timed(ltk_ctx *ctx, const double *d_alphas, int64_t B, double *d_lap,
                           void *d_workspace, size_t workspace_bytes, void *stream, float *h_ms);
 

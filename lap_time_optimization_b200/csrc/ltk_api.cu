@@ -22,17 +22,17 @@ struct ltk_ctx {
     VehDev veh;
     // scratch owned by the context
     int4* d_lut;  // engine cell table of the fused sweep (nullptr: none)
-    double* d_topk_lap;
-    long long* d_topk_idx;
+    double* d_topk_lap[2];  // ping-pong scratch of the top-k stages, grown on demand
+    long long* d_topk_idx[2];
+    long long topk_cap;     // entries per scratch buffer
     void* d_profile_ws;
     size_t profile_ws_bytes;
-    int k1_g_override, k1_staged_override, k1_threads_override, sweep_split;
+    int k1_g_override, k1_staged_override, k1_threads_override, sweep_split, sweep_mode;
     char err[256];
 };
 
 namespace {
 
-constexpr int TOPK_MAX_BLOCKS = 296;
 
 struct DeviceGuard {
     int prev = -1;
@@ -294,8 +294,9 @@ int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m
     a.staged = cfg.staged;
     if (ev) LTK_CUDA(ctx, cudaEventRecord(ev[0], st));
     LTK_CUDA(ctx, launch_k1a(ctx, a, st));
-    LTK_CUDA(ctx, launch_k1b_cfg(cfg, a, st));
     if (ev) LTK_CUDA(ctx, cudaEventRecord(ev[1], st));
+    LTK_CUDA(ctx, launch_k1b_cfg(cfg, a, st));
+    if (ev) LTK_CUDA(ctx, cudaEventRecord(ev[2], st));
 
     unsigned grid = (unsigned)((B + SWEEP_THREADS - 1) / SWEEP_THREADS);
     if (ctx->sweep_split && !dumps) {  // separate forward / backward kernels (A/B reference for the fused one)
@@ -311,10 +312,10 @@ int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m
         } else {
             k2_forward<1, 8><<<grid, SWEEP_THREADS, 0, st>>>(s, ctx->veh);
         }
-        if (ev) LTK_CUDA(ctx, cudaEventRecord(ev[2], st));
+        if (ev) LTK_CUDA(ctx, cudaEventRecord(ev[3], st));
         if (ctx->veh.kind == 0) k3_backward<0><<<grid, SWEEP_THREADS, 0, st>>>(s, ctx->veh);
         else k3_backward<1><<<grid, SWEEP_THREADS, 0, st>>>(s, ctx->veh);
-        if (ev) LTK_CUDA(ctx, cudaEventRecord(ev[3], st));
+        if (ev) LTK_CUDA(ctx, cudaEventRecord(ev[4], st));
         g_launches.fetch_add(2);
     } else {
         FusedArgs f;
@@ -327,17 +328,65 @@ int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m
         f.vmin_d = dumps ? reinterpret_cast<double*>(ws + w.vmin_off) : nullptr;
         f.ns = ctx->ns; f.B = B;
         unsigned gridf = (unsigned)((w.Bp + FUSED_THREADS - 1) / FUSED_THREADS);
-        if (ctx->veh.kind == 0) {
+        unsigned gridr = (unsigned)(w.Bp / 32);
+        // Small batches are latency-bound: one chain per thread, two warps per 32 candidates (K23r).
+        // From one resident wave upwards the two-chains-per-thread kernel is as fast or faster.
+        const bool roles = (ctx->sweep_mode == 2) || (ctx->sweep_mode == 0 && !dumps && B <= 16384);
+        if (roles) {
+            if (ctx->veh.kind == 0) {
+                if (ctx->veh.lut_top >= 0) k23_roles<0, 0><<<gridr, ROLES_THREADS, 0, st>>>(f, ctx->veh);
+                else if (ctx->veh.n_map <= 8) k23_roles<0, 8><<<gridr, ROLES_THREADS, 0, st>>>(f, ctx->veh);
+                else k23_roles<0, 16><<<gridr, ROLES_THREADS, 0, st>>>(f, ctx->veh);
+            } else {
+                k23_roles<1, 8><<<gridr, ROLES_THREADS, 0, st>>>(f, ctx->veh);
+            }
+        } else if (ctx->veh.kind == 0) {
             if (ctx->veh.lut_top >= 0) k23_sweep<0, 0><<<gridf, FUSED_THREADS, 0, st>>>(f, ctx->veh);
             else if (ctx->veh.n_map <= 8) k23_sweep<0, 8><<<gridf, FUSED_THREADS, 0, st>>>(f, ctx->veh);
             else k23_sweep<0, 16><<<gridf, FUSED_THREADS, 0, st>>>(f, ctx->veh);
         } else {
             k23_sweep<1, 8><<<gridf, FUSED_THREADS, 0, st>>>(f, ctx->veh);
         }
-        if (ev) { LTK_CUDA(ctx, cudaEventRecord(ev[2], st)); LTK_CUDA(ctx, cudaEventRecord(ev[3], st)); }
+        if (ev) { LTK_CUDA(ctx, cudaEventRecord(ev[3], st)); LTK_CUDA(ctx, cudaEventRecord(ev[4], st)); }
         g_launches.fetch_add(1);
     }
     LTK_CUDA(ctx, cudaGetLastError());
+    return LTK_OK;
+}
+
+// stages of topk_select until a single block writes the caller's buffers
+int run_topk(ltk_ctx* ctx, const double* d_lap, const long long* d_idx, long long count, long long index_base, int k,
+             double* d_best_lap, long long* d_best_idx, cudaStream_t st)
+{
+    long long blocks = (count + TOPK_BLOCK_KEYS - 1) / TOPK_BLOCK_KEYS;
+    if (blocks < 1) blocks = 1;
+    if (blocks > 1 && blocks * k > ctx->topk_cap) {  // grow the scratch (rare: first call / larger population)
+        LTK_CUDA(ctx, cudaStreamSynchronize(st));
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(ctx->d_topk_lap[i]); cudaFree(ctx->d_topk_idx[i]);
+            ctx->d_topk_lap[i] = nullptr; ctx->d_topk_idx[i] = nullptr;
+        }
+        ctx->topk_cap = 0;
+        const long long cap = blocks * TOPK_MAX;
+        for (int i = 0; i < 2; ++i) {
+            LTK_CUDA(ctx, cudaMalloc(&ctx->d_topk_lap[i], sizeof(double) * cap));
+            LTK_CUDA(ctx, cudaMalloc(&ctx->d_topk_idx[i], sizeof(long long) * cap));
+        }
+        ctx->topk_cap = cap;
+    }
+    int pp = 0;
+    while (true) {
+        const bool last = (blocks == 1);
+        double* o_lap = last ? d_best_lap : ctx->d_topk_lap[pp];
+        long long* o_idx = last ? d_best_idx : ctx->d_topk_idx[pp];
+        topk_select<<<(unsigned)blocks, TOPK_THREADS, 0, st>>>(d_lap, d_idx, count, index_base, k, o_lap, o_idx);
+        g_launches.fetch_add(1);
+        LTK_CUDA(ctx, cudaGetLastError());
+        if (last) break;
+        d_lap = o_lap; d_idx = o_idx; count = blocks * k; index_base = 0;
+        blocks = (count + TOPK_BLOCK_KEYS - 1) / TOPK_BLOCK_KEYS;
+        pp ^= 1;
+    }
     return LTK_OK;
 }
 
@@ -381,7 +430,11 @@ int ltk_create(ltk_ctx** out, int device, const double* h_left_xy, const double*
     if (const char* s = getenv("LTK_K1_G")) ctx->k1_g_override = atoi(s);
     if (const char* s = getenv("LTK_K1_STAGED")) ctx->k1_staged_override = atoi(s);
     ctx->sweep_split = 0;
-    if (const char* s = getenv("LTK_SWEEP")) ctx->sweep_split = (strcmp(s, "split") == 0);
+    ctx->sweep_mode = 0;
+    if (const char* s = getenv("LTK_SWEEP")) {
+        ctx->sweep_split = (strcmp(s, "split") == 0);
+        ctx->sweep_mode = (strcmp(s, "fused") == 0) ? 1 : (strcmp(s, "roles") == 0) ? 2 : 0;
+    }
     ctx->k1_threads_override = 0;
     if (const char* s = getenv("LTK_K1_THREADS")) {
         int t = atoi(s);
@@ -399,8 +452,6 @@ int ltk_create(ltk_ctx** out, int device, const double* h_left_xy, const double*
     }
     size_t bytes = sizeof(double) * 2 * (size_t)n_ctrl;
     if ((e = cudaMalloc(&ctx->d_left, bytes)) != cudaSuccess || (e = cudaMalloc(&ctx->d_diff, bytes)) != cudaSuccess ||
-        (e = cudaMalloc(&ctx->d_topk_lap, sizeof(double) * TOPK_MAX_BLOCKS * TOPK_MAX)) != cudaSuccess ||
-        (e = cudaMalloc(&ctx->d_topk_idx, sizeof(long long) * TOPK_MAX_BLOCKS * TOPK_MAX)) != cudaSuccess ||
         (e = cudaMemcpy(ctx->d_left, h_left_xy, bytes, cudaMemcpyHostToDevice)) != cudaSuccess ||
         (e = cudaMemcpy(ctx->d_diff, h_diff_xy, bytes, cudaMemcpyHostToDevice)) != cudaSuccess) {
         fail(nullptr, LTK_E_CUDA, "context allocation", e);
@@ -424,8 +475,7 @@ void ltk_destroy(ltk_ctx* ctx)
     cudaFree(ctx->d_left);
     cudaFree(ctx->d_diff);
     cudaFree(ctx->d_lut);
-    cudaFree(ctx->d_topk_lap);
-    cudaFree(ctx->d_topk_idx);
+    for (int i = 0; i < 2; ++i) { cudaFree(ctx->d_topk_lap[i]); cudaFree(ctx->d_topk_idx[i]); }
     cudaFree(ctx->d_profile_ws);
     delete ctx;
 }
@@ -473,15 +523,16 @@ int ltk_eval_alphas_timed(ltk_ctx* ctx, const double* d_alphas, int64_t B, doubl
     if (workspace_bytes < w.total) return fail(ctx, LTK_E_WORKSPACE, "workspace too small (see ltk_workspace_bytes)");
     DeviceGuard guard(ctx->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    cudaEvent_t ev[4];
-    for (int i = 0; i < 4; ++i) LTK_CUDA(ctx, cudaEventCreate(&ev[i]));
+    cudaEvent_t ev[5];
+    for (int i = 0; i < 5; ++i) LTK_CUDA(ctx, cudaEventCreate(&ev[i]));
     int rc = run_pipeline(ctx, d_alphas, nullptr, 0, B, d_lap, static_cast<char*>(d_workspace), w, false, st, ev);
     if (rc == LTK_OK) {
-        cudaError_t e = cudaEventSynchronize(ev[3]);
-        for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaEventElapsedTime(&h_ms[i], ev[i], ev[i + 1]);
+        cudaError_t e = cudaEventSynchronize(ev[4]);
+        for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventElapsedTime(&h_ms[i], ev[i], ev[i + 1]);
         if (e != cudaSuccess) rc = fail(ctx, LTK_E_CUDA, "event timing", e);
+        if (!ctx->sweep_split) h_ms[3] = -1.0f;  // one sweep kernel: no separate backward launch
     }
-    for (int i = 0; i < 4; ++i) cudaEventDestroy(ev[i]);
+    for (int i = 0; i < 5; ++i) cudaEventDestroy(ev[i]);
     return rc;
 }
 
@@ -492,12 +543,8 @@ int ltk_topk_pairs(ltk_ctx* ctx, const double* d_lap, const int64_t* d_idx, int6
     if (!d_lap || !d_idx || !d_best_lap || !d_best_idx || count < 0) return fail(ctx, LTK_E_ARG, "null or negative argument");
     if (k < 1 || k > TOPK_MAX) return fail(ctx, LTK_E_ARG, "k must be in 1..64");
     DeviceGuard guard(ctx->device);
-    topk_select<<<1, TOPK_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-        d_lap, reinterpret_cast<const long long*>(d_idx), count, count < 1 ? 1 : count, 0, k, d_best_lap,
-        reinterpret_cast<long long*>(d_best_idx));
-    g_launches.fetch_add(1);
-    LTK_CUDA(ctx, cudaGetLastError());
-    return LTK_OK;
+    return run_topk(ctx, d_lap, reinterpret_cast<const long long*>(d_idx), count, 0, k, d_best_lap,
+                    reinterpret_cast<long long*>(d_best_idx), static_cast<cudaStream_t>(stream));
 }
 
 int ltk_eval_controls(ltk_ctx* ctx, const double* d_xy, int m, int64_t B, double* d_lap, void* d_workspace,
@@ -556,25 +603,8 @@ int ltk_topk(ltk_ctx* ctx, const double* d_lap, int64_t B, int64_t index_base, i
     if (!d_lap || !d_best_lap || !d_best_idx || B < 0) return fail(ctx, LTK_E_ARG, "null or negative argument");
     if (k < 1 || k > TOPK_MAX) return fail(ctx, LTK_E_ARG, "k must be in 1..64");
     DeviceGuard guard(ctx->device);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    long long nblk = (B + 8191) / 8192;
-    if (nblk < 1) nblk = 1;
-    if (nblk > TOPK_MAX_BLOCKS) nblk = TOPK_MAX_BLOCKS;
-    long long chunk = (B + nblk - 1) / nblk;
-    if (chunk < 1) chunk = 1;
-    long long* out_idx = reinterpret_cast<long long*>(d_best_idx);
-    if (nblk == 1) {
-        topk_select<<<1, TOPK_THREADS, 0, st>>>(d_lap, nullptr, B, chunk, index_base, k, d_best_lap, out_idx);
-        g_launches.fetch_add(1);
-    } else {
-        topk_select<<<(unsigned)nblk, TOPK_THREADS, 0, st>>>(d_lap, nullptr, B, chunk, index_base, k, ctx->d_topk_lap,
-                                                             ctx->d_topk_idx);
-        topk_select<<<1, TOPK_THREADS, 0, st>>>(ctx->d_topk_lap, ctx->d_topk_idx, nblk * k, nblk * k, 0, k, d_best_lap,
-                                                out_idx);
-        g_launches.fetch_add(2);
-    }
-    LTK_CUDA(ctx, cudaGetLastError());
-    return LTK_OK;
+    return run_topk(ctx, d_lap, nullptr, B, index_base, k, d_best_lap, reinterpret_cast<long long*>(d_best_idx),
+                    static_cast<cudaStream_t>(stream));
 }
 
 int ltk_path_eval(int device, const double* d_xy, const double* d_knots, int m, const double* d_u, int64_t n,

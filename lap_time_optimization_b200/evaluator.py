@@ -104,17 +104,18 @@ class LapTimeEvaluator:
         """Average CUDA-event duration (ms) of each pipeline kernel over `reps` passes (measurement hook)."""
         B = alphas.shape[0]
         ws = self._workspace(B)
-        ms = (C.c_float * 3)()
-        acc = np.zeros(3)
+        ms = (C.c_float * 4)()
+        acc = np.zeros(4)
         for _ in range(reps):
             rc = self.lib.ltk_eval_alphas_timed(self._ctx, _device.ptr(alphas), B, _device.ptr(out), _device.ptr(ws),
                                                 ws.numel(), _device.stream_ptr(self.torch, self.device), ms)
             _native.check(rc, self._ctx)
             acc += np.array(ms[:])
         acc /= reps
-        if acc[2] < 1e-4:  # fused forward+backward sweep kernel (default)
-            return {"k1_curvature": float(acc[0]), "k23_sweep": float(acc[1])}
-        return {"k1_curvature": float(acc[0]), "k2_forward": float(acc[1]), "k3_backward": float(acc[2])}
+        if acc[3] < 0:  # one sweep kernel (forward and backward chains together; the default)
+            return {"k1a_spline_solve": float(acc[0]), "k1b_curvature": float(acc[1]), "k23_sweep": float(acc[2])}
+        return {"k1a_spline_solve": float(acc[0]), "k1b_curvature": float(acc[1]), "k2_forward": float(acc[2]),
+                "k3_backward": float(acc[3])}
 
     def merge_topk_device(self, laps, idx, k=DEFAULT_TOPK):
         """Stable ascending top-k of explicit (lap, global index) pairs (the multi-GPU merge)."""
@@ -163,6 +164,93 @@ class LapTimeEvaluator:
         self._pinned_out[:B].copy_(d_lap, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         return self._pinned_out[:B].numpy().copy()
+
+    def stream_populations(self, populations, k=DEFAULT_TOPK, index_base=0, index_stride=None, finish=None):
+        """Score a SEQUENCE of host populations with copies and kernels overlapped.
+
+        `populations` yields float64 arrays [B, n_alpha]: pinned torch tensors are copied as they are,
+        numpy arrays / pageable tensors go through a pinned staging buffer first.  Two slots are cycled:
+        while the kernels of population i run on the compute stream, the copy stream moves population
+        i+1 host->device and a second copy stream the results of population i-1 device->host.  Yields, in order, one
+        `(laps, best_laps, best_idx)` triple of numpy views per population; the views alias pinned slot
+        buffers and stay valid until two more results have been taken.  `finish(best, idx) ->
+        (best, idx)` runs on the compute stream after the local top-k (the multi-GPU all-gather + merge
+        hooks in here).  Candidate j of population i gets the global index index_base + i*index_stride + j
+        (index_stride defaults to the population size).  This is the path `bench.py` times as `e2e`."""
+        torch = self.torch
+        dev = self.device
+        compute = torch.cuda.current_stream(dev)
+        # one stream per direction: on a single in-order copy stream the upload of population i+1 would
+        # queue behind the download of population i, which waits for the kernels of population i
+        if getattr(self, "_copy_streams", None) is None:
+            self._copy_streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        copy, copy_out = self._copy_streams
+        nslot = 2
+        slots = [None] * nslot
+        pending = []  # (slot index, B) in submission order
+
+        def make_slot(B):
+            return {"B": B,
+                    "d_in": torch.empty((B, self.n_alpha), dtype=torch.float64, device=dev),
+                    "d_lap": torch.empty(B, dtype=torch.float64, device=dev),
+                    "h_stage": None,
+                    "h_lap": torch.empty(B, dtype=torch.float64).pin_memory(),
+                    "h_best": torch.empty(k, dtype=torch.float64).pin_memory(),
+                    "h_idx": torch.empty(k, dtype=torch.int64).pin_memory(),
+                    "ev_in": torch.cuda.Event(), "ev_done": torch.cuda.Event(), "ev_out": torch.cuda.Event(),
+                    "used": False}
+
+        def take(entry):
+            si, B = entry
+            sl = slots[si]
+            sl["ev_out"].synchronize()
+            return sl["h_lap"][:B].numpy(), sl["h_best"].numpy(), sl["h_idx"].numpy()
+
+        base = int(index_base)
+        for i, pop in enumerate(populations):
+            si = i % nslot
+            if len(pending) == nslot:  # the slot about to be reused still holds an untaken result
+                yield take(pending.pop(0))
+            t = pop if hasattr(pop, "is_pinned") else torch.from_numpy(np.ascontiguousarray(pop, dtype=np.float64))
+            if t.dim() != 2 or t.shape[1] != self.n_alpha or t.dtype != torch.float64:
+                raise ValueError(f"populations must be float64 [B, {self.n_alpha}]")
+            B = t.shape[0]
+            sl = slots[si]
+            if sl is None or sl["B"] < B or sl["h_best"].numel() != k:
+                sl = slots[si] = make_slot(B)
+            if not t.is_pinned():
+                if sl["h_stage"] is None or sl["h_stage"].shape[0] < B:
+                    sl["h_stage"] = torch.empty((B, self.n_alpha), dtype=torch.float64).pin_memory()
+                if sl["used"]:
+                    sl["ev_in"].synchronize()  # the previous H2D out of this staging buffer
+                sl["h_stage"][:B].copy_(t)
+                t = sl["h_stage"][:B]
+            with torch.cuda.stream(copy):
+                if sl["used"]:
+                    copy.wait_event(sl["ev_done"])  # kernels that read d_in / wrote d_lap of this slot
+                sl["d_in"][:B].copy_(t, non_blocking=True)
+                sl["ev_in"].record(copy)
+            compute.wait_event(sl["ev_in"])
+            if sl["used"]:
+                compute.wait_event(sl["ev_out"])  # d_lap of this slot has been read back
+            d_lap = self.lap_times_device(sl["d_in"][:B], out=sl["d_lap"][:B])
+            best, idx = self.topk_device(d_lap, k, index_base=base)
+            if finish is not None:
+                best, idx = finish(best, idx)
+            sl["ev_done"].record(compute)
+            with torch.cuda.stream(copy_out):
+                copy_out.wait_event(sl["ev_done"])
+                sl["h_lap"][:B].copy_(d_lap, non_blocking=True)
+                sl["h_best"].copy_(best, non_blocking=True)
+                sl["h_idx"].copy_(idx, non_blocking=True)
+                sl["ev_out"].record(copy_out)
+            # best/idx are read by the copy stream after this generator moves on: keep them alive
+            sl["keep"] = (best, idx)
+            sl["used"] = True
+            pending.append((si, B))
+            base += B if index_stride is None else int(index_stride)
+        while pending:
+            yield take(pending.pop(0))
 
     def topk_device(self, laps, k=DEFAULT_TOPK, index_base=0):
         """Stable ascending top-k of a CUDA lap tensor -> (lap[k], idx[k]) CUDA tensors."""

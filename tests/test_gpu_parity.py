@@ -161,6 +161,35 @@ def test_ragged_batches(buckmore, B):
     assert np.array_equal(ev.lap_times(a), co.lap_times(a))
 
 
+def test_stream_populations_matches_one_shot(buckmore):
+    """The pipelined host path (what bench.py times as e2e): pinned and pageable inputs, sizes that
+    change between populations, results in submission order and equal to the one-shot call."""
+    ev, co = buckmore
+    rng = np.random.default_rng(77)
+    sizes = [3000, 3000, 1, 4097, 3000, 64, 20000]
+    pops = [rng.uniform(0.0, 0.99, (b, ev.n_alpha)) for b in sizes]
+    feed = [torch.as_tensor(p).pin_memory() if i % 2 == 0 else p for i, p in enumerate(pops)]
+    base, seen = 1000, 0
+    for p, (laps, best, idx) in zip(pops, ev.stream_populations(iter(feed), k=10, index_base=base)):
+        want = co.lap_times(p)
+        assert np.array_equal(laps, want)
+        o_idx, o_best = top_k(list(want), 10)
+        n = min(10, len(p))
+        assert np.array_equal(best[:n], o_best[:n]) and np.array_equal(idx[:n], np.asarray(o_idx[:n]) + base)
+        base += len(p)
+        seen += 1
+    assert seen == len(pops)
+
+
+@pytest.mark.parametrize("B", [8192, 16384, 16385, 40000])
+def test_small_and_large_batch_sweep_kernels_agree(buckmore, B):
+    """<= 16,384 candidates run the one-chain-per-thread sweep (K23r), larger batches the two-chain one:
+    both must equal the oracle bit for bit on either side of the switch."""
+    ev, co = buckmore
+    a = np.random.default_rng(B).uniform(0.0, 0.99, (B, ev.n_alpha))
+    assert np.array_equal(ev.lap_times(a), co.lap_times(a))
+
+
 def test_empty_batch(buckmore):
     ev, _ = buckmore
     out = ev.lap_times_device(torch.empty((0, ev.n_alpha), dtype=torch.float64, device="cuda"))
