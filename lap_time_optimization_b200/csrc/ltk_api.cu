@@ -27,7 +27,7 @@ struct ltk_ctx {
     long long topk_cap;     // entries per scratch buffer
     void* d_profile_ws;
     size_t profile_ws_bytes;
-    int k1_g_override, k1_staged_override, k1_threads_override, sweep_split, sweep_mode;
+    int k1_g_override, k1_staged_override, k1_threads_override, sweep_split, sweep_mode, k1_mode;
     char err[256];
 };
 
@@ -262,6 +262,54 @@ cudaError_t launch_k1b(const K1Args& a, size_t smem, cudaStream_t st)
     return cudaGetLastError();
 }
 
+// K1b (ltk_spline.cuh): G candidates per CTA, T threads
+struct K1FConfig {
+    int G, threads;
+    size_t smem;
+};
+
+bool pick_k1f(const ltk_ctx* ctx, K1FConfig* out)
+{
+    if (ctx->k1_mode == 1) return false;  // LTK_K1=old: the previous K1a + K1b pair (A/B reference)
+    if (k1a_smem_bytes(ctx->N) > ctx->smem_optin) return false;
+    const int cand[3][2] = {{4, 128}, {4, 256}, {8, 256}};
+    for (int i = 0; i < 3; ++i) {
+        int G = cand[i][0], T = cand[i][1];
+        if (ctx->k1_g_override > 0 && G != ctx->k1_g_override) continue;
+        if (ctx->k1_threads_override > 0 && T != ctx->k1_threads_override) continue;
+        size_t s = k1f_smem_bytes(G, T, ctx->N, ctx->ns);
+        if (s <= ctx->smem_optin) { out->G = G; out->threads = T; out->smem = s; return true; }
+    }
+    return false;
+}
+
+template <int G, int T, int MINB>
+cudaError_t launch_k1f(const K1Args& a, size_t smem, cudaStream_t st)
+{
+    cudaError_t e = cudaFuncSetAttribute(k1b_samples<G, T, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k1b_samples<G, T, MINB><<<(unsigned)(a.Bp / G), T, smem, st>>>(a);
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_k1f_cfg(const K1FConfig& c, const K1Args& a, cudaStream_t st)
+{
+    if (c.G == 4 && c.threads == 128) return launch_k1f<4, 128, 5>(a, c.smem, st);
+    if (c.G == 4) return launch_k1f<4, 256, 4>(a, c.smem, st);
+    return launch_k1f<8, 256, 2>(a, c.smem, st);
+}
+
+cudaError_t launch_k1a_solve(const ltk_ctx* ctx, const K1Args& a, cudaStream_t st)
+{
+    size_t smem = k1a_smem_bytes(ctx->N);
+    cudaError_t e = cudaFuncSetAttribute(k1a_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k1a_solve<<<(unsigned)(a.Bp / 32), K1A_THREADS, smem, st>>>(a);
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_k1b_cfg(const K1Config& c, const K1Args& a, cudaStream_t st)
 {
     if (c.G == 16) {
@@ -280,7 +328,10 @@ int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m
                  cudaEvent_t* ev = nullptr)
 {
     K1Config cfg;
-    if (!pick_k1(ctx, &cfg)) return fail(ctx, LTK_E_UNSUPPORTED, "control-point count too large for shared memory");
+    K1FConfig fcfg;
+    const bool k1_one_kernel = pick_k1f(ctx, &fcfg);
+    if (!k1_one_kernel && !pick_k1(ctx, &cfg))
+        return fail(ctx, LTK_E_UNSUPPORTED, "control-point count too large for shared memory");
     K1Args a;
     a.alphas = d_alphas; a.xy = d_xy; a.mode = d_xy ? 1 : 0; a.m = m;
     a.left = ctx->d_left; a.diff = ctx->d_diff; a.N = ctx->N; a.ns = ctx->ns;
@@ -291,11 +342,18 @@ int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m
     a.mx = reinterpret_cast<double*>(ws + w.mx_off);
     a.my = reinterpret_cast<double*>(ws + w.my_off);
     a.knots = reinterpret_cast<double*>(ws + w.knots_off);
-    a.staged = cfg.staged;
     if (ev) LTK_CUDA(ctx, cudaEventRecord(ev[0], st));
-    LTK_CUDA(ctx, launch_k1a(ctx, a, st));
-    if (ev) LTK_CUDA(ctx, cudaEventRecord(ev[1], st));
-    LTK_CUDA(ctx, launch_k1b_cfg(cfg, a, st));
+    if (k1_one_kernel) {
+        a.staged = 1;
+        LTK_CUDA(ctx, launch_k1a_solve(ctx, a, st));
+        if (ev) LTK_CUDA(ctx, cudaEventRecord(ev[1], st));
+        LTK_CUDA(ctx, launch_k1f_cfg(fcfg, a, st));
+    } else {
+        a.staged = cfg.staged;
+        LTK_CUDA(ctx, launch_k1a(ctx, a, st));
+        if (ev) LTK_CUDA(ctx, cudaEventRecord(ev[1], st));
+        LTK_CUDA(ctx, launch_k1b_cfg(cfg, a, st));
+    }
     if (ev) LTK_CUDA(ctx, cudaEventRecord(ev[2], st));
 
     unsigned grid = (unsigned)((B + SWEEP_THREADS - 1) / SWEEP_THREADS);
@@ -430,6 +488,8 @@ int ltk_create(ltk_ctx** out, int device, const double* h_left_xy, const double*
     if (const char* s = getenv("LTK_K1_G")) ctx->k1_g_override = atoi(s);
     if (const char* s = getenv("LTK_K1_STAGED")) ctx->k1_staged_override = atoi(s);
     ctx->sweep_split = 0;
+    ctx->k1_mode = 0;
+    if (const char* s = getenv("LTK_K1")) ctx->k1_mode = (strcmp(s, "old") == 0) ? 1 : 0;
     ctx->sweep_mode = 0;
     if (const char* s = getenv("LTK_SWEEP")) {
         ctx->sweep_split = (strcmp(s, "split") == 0);
@@ -438,7 +498,7 @@ int ltk_create(ltk_ctx** out, int device, const double* h_left_xy, const double*
     ctx->k1_threads_override = 0;
     if (const char* s = getenv("LTK_K1_THREADS")) {
         int t = atoi(s);
-        if (t == 256 || t == 512 || t == 1024) ctx->k1_threads_override = t;
+        if (t == 128 || t == 256 || t == 512 || t == 1024) ctx->k1_threads_override = t;
     }
     int4 lut_cells[LTK_LUT_MAX_CELLS];
     const int n_cells = getenv("LTK_NO_ENGINE_LUT") ? 0 : build_engine_lut(*vehicle, &ctx->veh, lut_cells);

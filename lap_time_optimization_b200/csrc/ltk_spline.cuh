@@ -1,0 +1,304 @@
+// ltk_spline.cuh -- K1: alphas -> periodic cubic spline -> curvature at the samples.
+//
+//   reference: Track.control_points* (track.py:82-94), Path.__init__ -> splprep(k=3, s=0, per=1)
+//   (path.py:11-26), np.linspace sampling (tbn.py:71), Path.curvature (path.py:36-61), and the arg-min of
+//   v_local that both sweeps start from (velocity.py:34,58).
+//
+// Two kernels:
+//
+//   K1a k1a_solve     control points -> chord-length knots -> cyclic tridiagonal solve (Thomas +
+//                     Sherman-Morrison) for the second derivatives M_x, M_y.  A CTA is three warps over
+//                     the same 32 candidates: lane = candidate, warp = right-hand side (x | y | corner
+//                     vector).  The three warps repeat the pivot recurrence, so the serial part needs no
+//                     communication; scratch is five [N][32] arrays in shared memory (55 KB at N = 43,
+//                     four CTAs per SM).  Output: knots [N+1][Bp], M_x, M_y [N][Bp], candidate-minor.
+//   K1b k1b_samples   a CTA owns G = 4 candidates (one 32-byte sector of every 128-byte tile row):
+//                     per-interval cubic coefficients and the first sample index of every interval
+//                     (thread per interval), curvature (each thread walks a contiguous chunk of samples;
+//                     the interval switch is an integer test on the sample index), the tile in shared
+//                     memory, first maximum, write-out rotated so that row 0 of every candidate is its
+//                     own slowest sample.
+//
+// (Both were tried as ONE kernel with the solve on 3G lanes of each CTA: the ~15,000-cycle serial part
+// then idles the other warps of its CTA and the kernel took 0.51 ms against 0.10 + 0.30 ms for the
+// previous pair; see profiles/.)
+//
+// Arithmetic is the fixed sequence oracle/lap_oracle.c mirrors: IEEE + - * / sqrt, fma only where written.
+#pragma once
+
+namespace ltk {
+
+__host__ __device__ inline int k1_chunk(int n, int cpt)
+{
+    int c = (n + cpt - 1) / cpt;
+    return c | 1;  // odd: the per-thread rows of a warp then fall in distinct shared-memory banks
+}
+
+// doubles of scratch that alias the curvature tile (see the kernel for the carve-up)
+__host__ __device__ inline size_t k1f_scratch_doubles(int G, int N) { return (size_t)(5 * N + 1) * G; }
+
+__host__ __device__ inline size_t k1f_smem_bytes(int G, int threads, int N, int ns)
+{
+    size_t tile = (size_t)(ns - 1) * G, scr = k1f_scratch_doubles(G, N);
+    size_t bytes = (size_t)N * G * sizeof(Interval);                 // interval records [N][G]
+    bytes += (tile > scr ? tile : scr) * sizeof(double);             // curvature tile | scratch
+    bytes += (size_t)(N + 1) * G * sizeof(int) + 8;                  // first sample index of each interval (+ alignment)
+    bytes += (size_t)G * (sizeof(double) + sizeof(int));             // length, rotation
+    bytes += (size_t)(threads / 32) * G * (sizeof(double) + sizeof(int));  // arg-max partials
+    return (bytes + 15) / 16 * 16;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1a
+// ------------------------------------------------------------------------------------------------
+constexpr int K1A_THREADS = 96;  // warp = right-hand side, lane = candidate
+__host__ __device__ inline size_t k1a_smem_bytes(int N) { return (size_t)5 * N * 32 * sizeof(double); }
+
+__global__ void __launch_bounds__(K1A_THREADS, 4) k1a_solve(K1Args a)
+{
+    extern __shared__ __align__(16) double sm1[];
+    const int N = a.N, NL = N * 32;
+    double* RX = sm1;         // [N][32] control point x, then solution x, then M_x
+    double* RY = RX + NL;
+    double* RZ = RY + NL;     // corner-vector solution
+    double* H = RZ + NL;      // chord lengths, then interval widths as the spline sees them
+    double* CP = H + NL;      // modified super-diagonal
+    const int tid = threadIdx.x, lane = tid & 31, rhs = tid >> 5;
+    const long long b0 = (long long)blockIdx.x * 32;
+#define S1(A, j) A[(j) * 32 + lane]
+    // control points (track.py:87,:94): consecutive threads along a candidate's alpha row
+    for (int idx = tid; idx < NL; idx += K1A_THREADS) {
+        const int g = idx / N, j = idx - g * N;
+        long long b = b0 + g;
+        b = (b < a.B) ? b : a.B - 1;  // padding lanes repeat the last candidate
+        double x, y;
+        control_point(a, b, j, x, y);
+        RX[j * 32 + g] = x;
+        RY[j * 32 + g] = y;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < NL; idx += K1A_THREADS) {  // chord lengths (path.py:13)
+        const int j = idx >> 5, g = idx & 31;
+        const int jn = (j + 1 == N) ? 0 : j + 1;
+        const double ex = RX[jn * 32 + g] - RX[idx], ey = RY[jn * 32 + g] - RY[idx];
+        H[idx] = dsqrt<false>(ex * ex + ey * ey);
+    }
+    __syncthreads();
+    if (rhs == 0) {  // knots: np.cumsum order (path.py:14); interval widths are knot differences
+        const long long b = b0 + lane;
+        double acc = 0.0;
+        a.knots[b] = 0.0;
+        for (int j = 0; j < N; ++j) {
+            const double prev = acc;
+            acc = acc + S1(H, j);
+            a.knots[(size_t)(j + 1) * a.Bp + b] = acc;
+            S1(H, j) = acc - prev;
+        }
+    }
+    __syncthreads();
+    {
+        // forward elimination of this warp's right-hand side; row 0's corner term lives in the
+        // Sherman-Morrison vector
+        double* R = (rhs == 0) ? RX : (rhs == 1) ? RY : RZ;
+        const double hl = S1(H, N - 1), h0 = S1(H, 0);
+        const double b0d = 2.0 * (hl + h0);
+        const double gamma = -b0d;
+        const double p0 = (rhs < 2) ? S1(R, 0) : 0.0;
+        const double dl = (rhs < 2) ? ddiv<false>(p0 - S1(R, N - 1), hl) : 0.0;  // closing chord slope
+        double pj = p0, dprev = dl, hprev = 0.0, cp = 0.0, r = 0.0;
+        for (int j = 0; j < N; ++j) {
+            const double hj = S1(H, j);
+            double f;
+            if (rhs < 2) {
+                double dj = dl;
+                if (j + 1 < N) {
+                    const double pn = S1(R, j + 1);
+                    dj = ddiv<false>(pn - pj, hj);
+                    pj = pn;
+                }
+                f = 6.0 * (dj - dprev);
+                dprev = dj;
+            } else {
+                f = (j == 0) ? gamma : ((j == N - 1) ? hl : 0.0);
+            }
+            const double aa = hprev;
+            const double bbd = (j == 0) ? b0d - gamma : ((j == N - 1) ? 2.0 * (hprev + hl) - hl * hl / gamma : 2.0 * (aa + hj));
+            const double den = (j == 0) ? bbd : bbd - aa * cp;
+            const double inv = ddiv<false>(1.0, den);
+            cp = hj * inv;
+            r = (j == 0) ? f * inv : (f - aa * r) * inv;
+            S1(CP, j) = cp;  // the three warps store identical values
+            S1(R, j) = r;
+            hprev = hj;
+        }
+        for (int j = N - 2; j >= 0; --j) {  // back substitution
+            r = S1(R, j) - S1(CP, j) * r;
+            S1(R, j) = r;
+        }
+    }
+    __syncthreads();
+    if (rhs < 2) {  // Sherman-Morrison correction, store M_x / M_y
+        const long long b = b0 + lane;
+        const double* R = (rhs == 0) ? RX : RY;
+        double* out = (rhs == 0) ? a.mx : a.my;
+        const double hl = S1(H, N - 1);
+        const double gamma = -(2.0 * (hl + S1(H, 0)));
+        const double vN = hl / gamma;
+        const double denom = 1.0 + (S1(RZ, 0) + vN * S1(RZ, N - 1));
+        const double fs = (S1(R, 0) + vN * S1(R, N - 1)) / denom;
+        for (int j = 0; j < N; ++j) out[(size_t)j * a.Bp + b] = S1(R, j) - fs * S1(RZ, j);
+    }
+#undef S1
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1b
+// ------------------------------------------------------------------------------------------------
+template <int G, int T, int MINB>
+__global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a)
+{
+    static_assert(32 % G == 0 && T % 32 == 0, "lanes split evenly over the candidates of a CTA");
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int N = a.N, n = a.ns - 1, NG = N * G;
+    constexpr int NW = T / 32, CPT = T / G;
+    Interval* REC = reinterpret_cast<Interval*>(smraw);
+    double* KT = reinterpret_cast<double*>(REC + NG);
+    const size_t tile = (size_t)n * G, scr = k1f_scratch_doubles(G, N);
+    int* IB = reinterpret_cast<int*>(KT + (tile > scr ? tile : scr));   // [N+1][G]
+    double* LEN = reinterpret_cast<double*>(IB + (N + 1) * G + (((N + 1) * G) & 1));
+    double* RV = LEN + G;                                               // [NW][G]
+    int* RI = reinterpret_cast<int*>(RV + NW * G);                      // [NW][G]
+    int* ROT = RI + NW * G;                                             // [G]
+    // scratch inside the tile region (dead before the first curvature is stored)
+    double* PX = KT;                 // [N][G] control points
+    double* PY = PX + NG;
+    double* U = PY + NG;             // [N+1][G] knots
+    double* RX = U + NG + G;         // [N][G] second derivatives M_x, M_y
+    double* RY = RX + NG;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long b0 = (long long)blockIdx.x * G;
+
+    // ---- L: control points from the alphas; knots and second derivatives from K1a ----------------------
+    for (int idx = tid; idx < NG; idx += T) {
+        const int g = idx / N, j = idx - g * N;  // j fastest: a candidate's alpha row is contiguous
+        long long b = b0 + g;
+        b = (b < a.B) ? b : a.B - 1;             // padding lanes repeat the last candidate
+        double x, y;
+        control_point(a, b, j, x, y);
+        PX[j * G + g] = x;
+        PY[j * G + g] = y;
+    }
+    for (int idx = tid; idx < NG + G; idx += T) {
+        const int j = idx / G, g = idx - j * G;
+        U[idx] = a.knots[(size_t)j * a.Bp + b0 + g];
+        if (j < N) {
+            RX[idx] = a.mx[(size_t)j * a.Bp + b0 + g];
+            RY[idx] = a.my[(size_t)j * a.Bp + b0 + g];
+        }
+    }
+    if (tid < G) LEN[tid] = a.knots[(size_t)N * a.Bp + b0 + tid];
+    __syncthreads();
+    // ---- C: per-interval coefficients  S'(t) = c1 + t (c2 + t h),  S''(t) = c2 + c3 t,  h = c3/2, and the
+    //      first sample index of every interval: IB[j] = min{ i : fl(i*step) >= U[j] } ------------------
+    for (int idx = tid; idx < NG; idx += T) {
+        const int j = idx / G, g = idx - j * G;
+        const int jn = (j + 1 == N) ? 0 : j + 1;
+        const double u0 = U[idx], u1 = U[idx + G], h = u1 - u0;  // the spline only sees the knots
+        const double mx = RX[idx], mxn = RX[jn * G + g];
+        const double my = RY[idx], myn = RY[jn * G + g];
+        const double c3x = ddiv<false>(mxn - mx, h), c3y = ddiv<false>(myn - my, h);
+        Interval rec;
+        rec.u = u0; rec.unext = u1;
+        rec.c1x = ddiv<false>(PX[jn * G + g] - PX[idx], h) - ddiv<false>(h * (2.0 * mx + mxn), 6.0);
+        rec.c1y = ddiv<false>(PY[jn * G + g] - PY[idx], h) - ddiv<false>(h * (2.0 * my + myn), 6.0);
+        rec.c2x = mx; rec.c2y = my;
+        rec.c3x = c3x; rec.c3y = c3y;
+        rec.hx = 0.5 * c3x; rec.hy = 0.5 * c3y;
+        REC[idx] = rec;
+        const double step = LEN[g] / (double)(a.ns - 1);  // np.linspace step (tbn.py:71)
+        int i = 0;
+        if (j > 0) {
+            i = (int)ddiv<false>(u0, step);
+            i = max(0, min(i, n));
+            while (i < n && (double)i * step < u0) ++i;
+            while (i > 0 && (double)(i - 1) * step >= u0) --i;
+        }
+        IB[idx] = i;
+        if (j == N - 1) IB[NG + g] = n;
+    }
+    __syncthreads();  // scratch is dead from here on: the tile region now takes curvatures
+
+    // ---- K: curvature at the samples ----------------------------------------------------------------------
+    const int g = tid % G, c = tid / G;
+    const int chunk = k1_chunk(n, CPT);
+    const int i0 = min(n, c * chunk), i1 = min(n, i0 + chunk);
+    const double step = LEN[g] / (double)(a.ns - 1);
+    double best = -1.0;
+    int bi = 0;
+    if (i0 < i1) {
+        int lo = 0, hi = N - 1;  // interval of sample i0: largest j with IB[j] <= i0
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (IB[mid * G + g] <= i0) lo = mid; else hi = mid - 1;
+        }
+        // One flat loop per chunk: every lane of the warp runs the same number of iterations (nested
+        // per-interval loops diverge -- interval boundaries differ from lane to lane -- and ran at 19 of
+        // 32 lanes); the interval switch is an integer test that fires about once per 20 samples.
+        int j = lo;
+        Interval v = REC[j * G + g];
+        int inext = IB[(j + 1) * G + g];
+        for (int i = i0; i < i1; ++i) {
+            while (i >= inext) {
+                ++j;
+                v = REC[j * G + g];
+                inext = IB[(j + 1) * G + g];
+            }
+            // |x'y'' - y'x''| / (x'^2 + y'^2)^(3/2)   (path.py:58,61), Horner form, explicit FMAs
+            const double s = (double)i * step;
+            const double t = s - v.u;
+            const double ddx = fma(v.c3x, t, v.c2x), ddy = fma(v.c3y, t, v.c2y);
+            const double dx = fma(t, fma(v.hx, t, v.c2x), v.c1x);
+            const double dy = fma(t, fma(v.hy, t, v.c2y), v.c1y);
+            const double cross = fabs(fma(dx, ddy, -(dy * ddx)));
+            const double n2 = fma(dx, dx, dy * dy);
+            const double k = ddiv<false>(cross, n2 * dsqrt<false>(n2));
+            KT[(size_t)i * G + g] = k;
+            if (k > best) { best = k; bi = i; }
+        }
+    }
+    // first maximum of the curvature == a minimum of v_local (velocity.py:34).  Lanes l, l+G, l+2G, ...
+    // hold consecutive chunks of one candidate: fold the upper lanes into the lower ones, lower chunk first
+#pragma unroll
+    for (int o = G; o < 32; o <<= 1) {
+        const double ob = __shfl_down_sync(0xffffffffu, best, o);
+        const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+        if ((lane % (2 * o)) < o && lane + o < 32 && ob > best) { best = ob; bi = oi; }
+    }
+    if (lane < G) { RV[warp * G + lane] = best; RI[warp * G + lane] = bi; }
+    __syncthreads();
+    if (tid < G) {
+        double bb = -1.0;
+        int bbi = 0;
+        for (int w = 0; w < NW; ++w) {
+            const double v = RV[w * G + tid];
+            if (v > bb) { bb = v; bbi = RI[w * G + tid]; }
+        }
+        ROT[tid] = bbi;
+        a.rot[b0 + tid] = bbi;
+        a.len[b0 + tid] = LEN[tid];
+    }
+    __syncthreads();
+    // ---- W: write-out, rotated: row i of candidate g is sample (i + rot_g) mod n ----------------------------
+    {
+        const int q0 = ROT[g];
+        double* dst = a.kap + tile_base(b0 + g, n);
+        for (int i = c; i < n; i += CPT) {
+            int q = i + q0;
+            q = (q >= n) ? q - n : q;
+            dst[(size_t)i * TILE] = KT[(size_t)q * G + g];
+        }
+    }
+}
+
+}  // namespace ltk
