@@ -33,7 +33,7 @@
 namespace ltk {
 
 constexpr int FUSED_THREADS = 64;
-constexpr int FUSED_UNROLL = 4;
+constexpr int FUSED_UNROLL = 2;
 constexpr unsigned FULL_MASK = 0xffffffffu;
 
 struct FusedArgs {
@@ -99,10 +99,10 @@ __device__ __forceinline__ double forward_fast(const VehDev& V, const FusedShare
     double w = v_prev * v_prev;
     double tr = traction_from<false>(V, lateral_force<KIND>(V, v_prev, w, k_prev));
     double en = (KIND == 0) ? engine_fast<ENG>(V, S, v_prev) : V.e0 - V.cr2 * w;
-    double force = (en < tr) ? en : tr;
+    double force = lt_nonneg<false>(en, tr) ? en : tr;
     double accel2 = div_by_const<false>(force, V.half_mass, V.inv_half_mass);
     double wlim = w + accel2 * ds;
-    return dsqrt<false>((wlim < wl) ? wlim : wl);
+    return dsqrt<false>(lt_nonneg<false>(wlim, wl) ? wlim : wl);
 }
 
 // velocity.py:68-73, same transformation
@@ -113,7 +113,7 @@ __device__ __forceinline__ double backward_fast(const VehDev& V, double v_next, 
     double tr = traction_from<false>(V, lateral_force<KIND>(V, v_next, w, k_next));
     double decel2 = div_by_const<false>(tr, V.half_mass, V.inv_half_mass);
     double wlim = w + decel2 * ds;
-    return dsqrt<false>((wlim < wl) ? wlim : wl);
+    return dsqrt<false>(lt_nonneg<false>(wlim, wl) ? wlim : wl);
 }
 
 // state of the two chains of one candidate
@@ -161,6 +161,45 @@ __device__ __forceinline__ double clock_retreat(Chains& c)
     return ds;
 }
 
+// Two square roots / one forward and one backward step written stage by stage for BOTH operands: a warp
+// issues in order, so the two dependency chains only overlap as far as the instruction stream
+// alternates between them.  Left to itself the compiler emitted the forward step and the backward step
+// largely one after the other (a lone warp needed ~600 cycles per row pair, more than the two chains'
+// latencies added up); written in pairs it alternates.  Same operations, same results.
+__device__ __forceinline__ void dsqrt_pair(double x0, double x1, double& r0, double& r1)
+{
+    double y0 = rsqrt_seed(x0), y1 = rsqrt_seed(x1);
+    double t0 = y0 * y0, t1 = y1 * y1;
+    double e0 = fma(x0, -t0, 1.0), e1 = fma(x1, -t1, 1.0);
+    double p0 = fma(e0, 0.375, 0.5), p1 = fma(e1, 0.375, 0.5);
+    double q0 = p0 * e0, q1 = p1 * e1;
+    y0 = fma(y0, q0, y0); y1 = fma(y1, q1, y1);
+    double g0 = x0 * y0, g1 = x1 * y1;
+    double s0 = fma(g0, -g0, x0), s1 = fma(g1, -g1, x1);
+    r0 = fma(s0, half_of(y0), g0); r1 = fma(s1, half_of(y1), g1);
+}
+
+template <int KIND, int ENG>
+__device__ __forceinline__ void step_pair_fast(const VehDev& V, const FusedShared& S, double vf, double kf, double wlf,
+                                               double ds_f, double vb, double kb, double wlb, double ds_b,
+                                               double& va, double& vd)
+{
+    const double wf = vf * vf, wb = vb * vb;
+    const double en = (KIND == 0) ? engine_fast<ENG>(V, S, vf) : V.e0 - V.cr2 * wf;  // forward chain only
+    const double lf = lateral_force<KIND>(V, vf, wf, kf), lb = lateral_force<KIND>(V, vb, wb, kb);
+    const double xf = V.f_max_sq - lf * lf, xb = V.f_max_sq - lb * lb;  // vehicle.py:35
+    double tf, tb;
+    dsqrt_pair(xf, xb, tf, tb);
+    tf = le_nonneg<false>(V.f_max, lf) ? 0.0 : tf;                       // vehicle.py:33-34
+    tb = le_nonneg<false>(V.f_max, lb) ? 0.0 : tb;
+    const double force = lt_nonneg<false>(en, tf) ? en : tf;
+    const double af = div_by_const<false>(force, V.half_mass, V.inv_half_mass);
+    const double ab = div_by_const<false>(tb, V.half_mass, V.inv_half_mass);
+    const double limf = wf + af * ds_f, limb = wb + ab * ds_b;
+    const double nf = lt_nonneg<false>(limf, wlf) ? limf : wlf, nb = lt_nonneg<false>(limb, wlb) ? limb : wlb;
+    dsqrt_pair(nf, nb, va, vd);
+}
+
 // U row pairs on the regular path.  PHASE 1 parks, PHASE 2 meets the parked values and accumulates.
 template <int KIND, int ENG, int PHASE, bool WRAP>
 __device__ __forceinline__ void fused_block(const VehDev& V, const FusedShared& S, Chains& c,
@@ -178,16 +217,16 @@ __device__ __forceinline__ void fused_block(const VehDev& V, const FusedShared& 
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-        double va = forward_fast<KIND, ENG>(V, S, c.vf, c.kf, wlf[u], c.ds_f);
+        const double ds_b = clock_retreat<WRAP>(c);
+        double va, vd;
+        step_pair_fast<KIND, ENG>(V, S, c.vf, c.kf, wlf[u], c.ds_f, c.vb, c.kb, wlb[u], ds_b, va, vd);
         c.ds_f = clock_advance<WRAP>(c);
-        double ds_b = clock_retreat<WRAP>(c);
-        double vd = backward_fast<KIND>(V, c.vb, c.kb, wlb[u], ds_b);
         if (PHASE == 1) {
             sfp[(size_t)u * P] = va;
             *(sbp - (size_t)u * P) = vd;
         } else {
-            double v1 = (va < fo[u]) ? va : fo[u];  // velocity.py:26
-            double v2 = (bo[u] < vd) ? bo[u] : vd;
+            double v1 = lt_nonneg<false>(va, fo[u]) ? va : fo[u];  // velocity.py:26
+            double v2 = lt_nonneg<false>(bo[u], vd) ? bo[u] : vd;
             c.lap_f = c.lap_f + ddiv<false>(c.ds_f, v1);  // tbn.py:53
             c.lap_b = c.lap_b + ddiv<false>(ds_b, v2);
         }

@@ -96,7 +96,7 @@ __device__ __forceinline__ void chain_block(const VehDev& V, const FusedShared& 
             if (PHASE == 1) {
                 sp[u * D] = va;
             } else {
-                double v1 = (va < oc[u]) ? va : oc[u];         // velocity.py:26
+                double v1 = lt_nonneg<false>(va, oc[u]) ? va : oc[u];         // velocity.py:26
                 c.lap = c.lap + ddiv<false>(c.ds, v1);         // tbn.py:53
             }
             c.v = va;
@@ -106,7 +106,7 @@ __device__ __forceinline__ void chain_block(const VehDev& V, const FusedShared& 
             if (PHASE == 1) {
                 sp[u * D] = vd;
             } else {
-                double v2 = (oc[u] < vd) ? oc[u] : vd;
+                double v2 = lt_nonneg<false>(oc[u], vd) ? oc[u] : vd;
                 c.lap = c.lap + ddiv<false>(ds, v2);
             }
             c.v = vd;

@@ -280,9 +280,30 @@ def _eval_rows(rows):
     return [_WORKER.lap_time(a) for a in rows]
 
 
+class LapPool:
+    """A persistent fork pool of `processes` workers, one reference-equivalent evaluator each."""
+
+    def __init__(self, track_json, width, vehicle_json, mode="bayes", ns=None, processes=None):
+        import multiprocessing as mp
+        import os
+
+        self.processes = processes or os.cpu_count() or 1
+        self.pool = mp.get_context("fork").Pool(self.processes, initializer=_init_worker,
+                                                 initargs=(track_json, width, vehicle_json, mode, ns))
+
+    def lap_times(self, alphas):
+        alphas = np.asarray(alphas, dtype=np.float64)
+        chunks = np.array_split(alphas, min(len(alphas), self.processes * 8))
+        out = self.pool.map(_eval_rows, chunks)
+        return np.asarray([x for part in out for x in part])
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
 def lap_times_pool(track_json, width, vehicle_json, alphas, mode="bayes", ns=None, processes=None):
     """Score the rows of `alphas` with `processes` worker processes; returns laps[B]."""
-    import multiprocessing as mp
     import os
 
     processes = processes or os.cpu_count()
@@ -290,9 +311,8 @@ def lap_times_pool(track_json, width, vehicle_json, alphas, mode="bayes", ns=Non
     if processes <= 1:
         _init_worker(track_json, width, vehicle_json, mode, ns)
         return np.asarray(_eval_rows(alphas))
-    chunks = np.array_split(alphas, min(len(alphas), processes * 8))
-    ctx = mp.get_context("fork")
-    with ctx.Pool(processes, initializer=_init_worker,
-                  initargs=(track_json, width, vehicle_json, mode, ns)) as pool:
-        out = pool.map(_eval_rows, chunks)
-    return np.asarray([x for part in out for x in part])
+    pool = LapPool(track_json, width, vehicle_json, mode, ns, processes)
+    try:
+        return pool.lap_times(alphas)
+    finally:
+        pool.close()
