@@ -41,7 +41,7 @@ N_INPUT_SETS = 8  # distinct resident populations cycled through the steps (8 x 
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=200)
+    p.add_argument("--steps", type=int, default=500)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--candidates", type=int, default=65536, help="candidates per GPU per step")
