@@ -269,9 +269,9 @@ class LapTimeEvaluator:
                     lane.stream.wait_event(sl["ev_out"])  # d_lap of this slot has been read back
                 d_lap = lane.ev.lap_times_device(sl["d_in"][:B], out=sl["d_lap"][:B])
                 best, idx = lane.ev.topk_device(d_lap, k, index_base=base)
-                if finish is not None:
-                    best, idx = finish(best, idx)
                 sl["ev_done"].record(lane.stream)
+            if finish is not None:
+                best, idx = self._finish_async(finish, best, idx, sl["ev_done"])
             with torch.cuda.stream(copy_out):
                 copy_out.wait_event(sl["ev_done"])
                 sl["h_lap"][:B].copy_(d_lap, non_blocking=True)
@@ -304,12 +304,31 @@ class LapTimeEvaluator:
                 d_lap = lane.ev.lap_times_device(pop, out=outs[i % len(pool)])
                 last = lane.ev.topk_device(d_lap, k, index_base=index_base)
                 if finish is not None:
-                    last = finish(*last)
-        for lane in pool:
+                    done = torch.cuda.Event()
+                    done.record(lane.stream)
+            if finish is not None:
+                last = self._finish_async(finish, last[0], last[1], done)
+        for st in [lane.stream for lane in pool] + ([self._comm_stream] if finish is not None else []):
             done = torch.cuda.Event()
-            done.record(lane.stream)
+            done.record(st)
             main.wait_event(done)
         return last
+
+    def _finish_async(self, finish, best, idx, ready):
+        """Run the cross-rank step (all-gather + merge) of one population on a communication stream of its
+        own: the lane that produced (best, idx) goes straight on to its next population instead of
+        waiting out the collective's latency.  `ready` is re-recorded when the result is complete."""
+        torch = self.torch
+        if getattr(self, "_comm_stream", None) is None:
+            self._comm_stream = torch.cuda.Stream(self.device)
+        comm = self._comm_stream
+        with torch.cuda.stream(comm):
+            comm.wait_event(ready)
+            best.record_stream(comm)
+            idx.record_stream(comm)
+            out = finish(best, idx)
+            ready.record(comm)
+        return out
 
     def topk_device(self, laps, k=DEFAULT_TOPK, index_base=0):
         """Stable ascending top-k of a CUDA lap tensor -> (lap[k], idx[k]) CUDA tensors."""
