@@ -89,6 +89,13 @@ int ltk_eval_alphas(ltk_ctx *ctx, const double *d_alphas, int64_t B, double *d_l
 int ltk_eval_alphas_timed(ltk_ctx *ctx, const double *d_alphas, int64_t B, double *d_lap,
                           void *d_workspace, size_t workspace_bytes, void *stream, float *h_ms);
 
+/* alphas -> curvature objectives of the same spline: d_gamma2[B] = sum of squared curvatures at ALL ns
+ * samples (Path.gamma2(self.s), path.py:63-77 as called from trajectory.py:60-97), d_length[B] =
+ * Path.length (path.py:26).  Either output may be NULL.  Replaces, per candidate, the objective of
+ * Trajectory.minimise_curvature / minimise_compromise.  Kernels: K1a, K1b, one reduction. */
+int ltk_eval_objectives(ltk_ctx *ctx, const double *d_alphas, int64_t B, double *d_gamma2,
+                        double *d_length, void *d_workspace, size_t workspace_bytes, void *stream);
+
 /* control points -> lap times: the calcMinTime(controls) surface
  * (trajectory_bayesian_nonlinear.py:65-80).  d_xy [B][2][m] row-major with m = n_ctrl + 1 columns
  * (the last column is the closing duplicate and is ignored, exactly as splprep(per=1) overwrites it). */

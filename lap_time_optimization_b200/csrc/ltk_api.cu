@@ -322,10 +322,20 @@ cudaError_t launch_k1b_cfg(const K1Config& c, const K1Args& a, cudaStream_t st)
     return launch_k1b<8, 512>(a, c.smem, st);
 }
 
-// the three pipeline launches on a laid-out workspace
+int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m, long long B, double* d_lap, char* ws,
+                 const WsLayout& w, bool dumps, cudaStream_t st, cudaEvent_t* ev, bool k1_only);
+
+// the pipeline launches on a laid-out workspace
 int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m, long long B,
                  double* d_lap, char* ws, const WsLayout& w, bool dumps, cudaStream_t st,
                  cudaEvent_t* ev = nullptr)
+{
+    return run_pipeline(ctx, d_alphas, d_xy, m, B, d_lap, ws, w, dumps, st, ev, false);
+}
+
+int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m, long long B,
+                 double* d_lap, char* ws, const WsLayout& w, bool dumps, cudaStream_t st,
+                 cudaEvent_t* ev, bool k1_only)
 {
     K1Config cfg;
     K1FConfig fcfg;
@@ -355,6 +365,7 @@ int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m
         LTK_CUDA(ctx, launch_k1b_cfg(cfg, a, st));
     }
     if (ev) LTK_CUDA(ctx, cudaEventRecord(ev[2], st));
+    if (k1_only) return LTK_OK;
 
     unsigned grid = (unsigned)((B + SWEEP_THREADS - 1) / SWEEP_THREADS);
     if (ctx->sweep_split && !dumps) {  // separate forward / backward kernels (A/B reference for the fused one)
@@ -594,6 +605,27 @@ int ltk_eval_alphas_timed(ltk_ctx* ctx, const double* d_alphas, int64_t B, doubl
     }
     for (int i = 0; i < 5; ++i) cudaEventDestroy(ev[i]);
     return rc;
+}
+
+int ltk_eval_objectives(ltk_ctx* ctx, const double* d_alphas, int64_t B, double* d_gamma2, double* d_length,
+                        void* d_workspace, size_t workspace_bytes, void* stream)
+{
+    if (!ctx) return LTK_E_ARG;
+    if (B == 0) return LTK_OK;
+    if (!d_alphas || (!d_gamma2 && !d_length) || !d_workspace || B < 0) return fail(ctx, LTK_E_ARG, "null or negative argument");
+    WsLayout w = ws_layout(ctx->ns, ctx->N, B, false);
+    if (workspace_bytes < w.total) return fail(ctx, LTK_E_WORKSPACE, "workspace too small (see ltk_workspace_bytes)");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char* ws = static_cast<char*>(d_workspace);
+    int rc = run_pipeline(ctx, d_alphas, nullptr, 0, B, nullptr, ws, w, false, st, nullptr, true);
+    if (rc != LTK_OK) return rc;
+    curvature_objectives<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(
+        reinterpret_cast<double*>(ws + w.kap_off), reinterpret_cast<int*>(ws + w.rot_off),
+        reinterpret_cast<double*>(ws + w.len_off), ctx->ns, B, d_gamma2, d_length);
+    g_launches.fetch_add(1);
+    LTK_CUDA(ctx, cudaGetLastError());
+    return LTK_OK;
 }
 
 int ltk_topk_pairs(ltk_ctx* ctx, const double* d_lap, const int64_t* d_idx, int64_t count, int k, double* d_best_lap,

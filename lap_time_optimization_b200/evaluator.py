@@ -147,6 +147,37 @@ class LapTimeEvaluator:
         return {"k1a_spline_solve": float(acc[0]), "k1b_curvature": float(acc[1]), "k2_forward": float(acc[2]),
                 "k3_backward": float(acc[3])}
 
+    def curvature_objectives_device(self, alphas):
+        """alphas: float64 CUDA tensor [B, n_alpha] -> (gamma2[B], length[B]) CUDA tensors: the sum of squared
+        sample curvatures `Path.gamma2(s)` and `Path.length` of every candidate's spline (the objectives of
+        `Trajectory.minimise_curvature` / `minimise_compromise`, trajectory.py:60-97)."""
+        torch = self.torch
+        if alphas.dtype != torch.float64 or not alphas.is_cuda:
+            raise ValueError("alphas must be a float64 CUDA tensor")
+        alphas = alphas.contiguous()
+        if alphas.dim() != 2 or alphas.shape[1] != self.n_alpha:
+            raise ValueError(f"alphas must be [B, {self.n_alpha}]")
+        B = alphas.shape[0]
+        g2 = torch.empty(B, dtype=torch.float64, device=self.device)
+        length = torch.empty(B, dtype=torch.float64, device=self.device)
+        chunk = self.max_batch()
+        st = _device.stream_ptr(torch, self.device)
+        for lo in range(0, B, chunk):
+            hi = min(B, lo + chunk)
+            ws = self._workspace(hi - lo)
+            rc = self.lib.ltk_eval_objectives(self._ctx, _device.ptr(alphas[lo:hi]), hi - lo, _device.ptr(g2[lo:hi]),
+                                              _device.ptr(length[lo:hi]), _device.ptr(ws), ws.numel(), st)
+            _native.check(rc, self._ctx)
+        return g2, length
+
+    def curvature_objectives(self, alphas):
+        """Host in, host out version of `curvature_objectives_device`."""
+        a = np.ascontiguousarray(alphas, dtype=np.float64)
+        if a.ndim == 1:
+            a = a.reshape(1, -1)
+        g2, length = self.curvature_objectives_device(_device.to_device(a, self.device))
+        return g2.cpu().numpy(), length.cpu().numpy()
+
     def merge_topk_device(self, laps, idx, k=DEFAULT_TOPK):
         """Stable ascending top-k of explicit (lap, global index) pairs (the multi-GPU merge)."""
         torch = self.torch

@@ -6,6 +6,7 @@ the CUDA pipeline for one candidate); `lap_time_batch` scores a whole population
 from __future__ import annotations
 
 import math
+import time
 
 import numpy as np
 
@@ -66,3 +67,62 @@ class Trajectory:
         if isinstance(alphas, np.ndarray) or not hasattr(alphas, "is_cuda"):
             return self.evaluator.lap_times(alphas)
         return self.evaluator.lap_times_device(alphas)
+
+    def curvature_objectives_batch(self, alphas):
+        """alphas [B, track.size] -> (gamma2[B], length[B]): `path.gamma2(self.s)` and `path.length`
+        (trajectory.py:60-97) of every candidate, one pipeline pass."""
+        return self.evaluator.curvature_objectives(alphas)
+
+    # -- optimisers: the reference's objectives with batched finite-difference gradients -------------
+    # The reference hands `objfun` to scipy's L-BFGS-B without a gradient (trajectory.py:60-146), so scipy
+    # differences it itself: N + 1 = 132 sequential evaluations per gradient.  Here the same 2-point
+    # scheme (absolute step 1e-8, flipped where it would leave the box -- scipy's `approx_derivative`
+    # with `abs_step` and bounds) is ONE batch of N + 1 candidates on the GPU.
+    FD_STEP = 1e-8
+
+    def _fd_points(self, x, lo=0.0, hi=1.0):
+        x = np.asarray(x, dtype=np.float64)
+        h = np.full(x.size, self.FD_STEP)
+        h[x + h > hi] *= -1.0
+        pts = np.repeat(x[None, :], x.size + 1, axis=0)
+        idx = np.arange(x.size)
+        pts[idx + 1, idx] = x + h
+        dx = pts[idx + 1, idx] - x  # the step actually taken, as scipy does
+        return pts, dx
+
+    def _minimise(self, batch_objective):
+        from scipy.optimize import Bounds, minimize
+
+        def fun(x):
+            pts, dx = self._fd_points(x)
+            f = batch_objective(pts)
+            return float(f[0]), (f[1:] - f[0]) / dx
+
+        t0 = time.time()
+        res = minimize(fun=fun, x0=np.full(self.track.size, 0.5), jac=True, method="L-BFGS-B", bounds=Bounds(0.0, 1.0))
+        self.update(res.x)
+        self.result = res
+        return time.time() - t0
+
+    def lap_time_and_gradient(self, alphas):
+        """Lap time and its forward-difference gradient at `alphas`: one batch of N + 1 candidates."""
+        pts, dx = self._fd_points(alphas)
+        f = self.evaluator.lap_times(pts)
+        return f[0], (f[1:] - f[0]) / dx
+
+    def minimise_curvature(self):
+        """Generate a path minimising curvature (trajectory.py:60-75)."""
+        return self._minimise(lambda pts: self.evaluator.curvature_objectives(pts)[0])
+
+    def minimise_compromise(self, eps):
+        """Compromise between curvature and path length, `eps` weighs the length (trajectory.py:77-97)."""
+
+        def obj(pts):
+            k, d = self.evaluator.curvature_objectives(pts)
+            return (1 - eps) * k + eps * d
+
+        return self._minimise(obj)
+
+    def minimise_lap_time(self):
+        """Generate a path that directly minimises lap time (trajectory.py:128-146)."""
+        return self._minimise(self.evaluator.lap_times)

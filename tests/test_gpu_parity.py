@@ -317,3 +317,52 @@ def test_errors(buckmore):
     assert rc == _native.LTK_E_WORKSPACE and b"workspace" in ev.lib.ltk_last_error(ev._ctx)
     with pytest.raises(ltk.LtkError):
         ev.topk(np.zeros(4), 65)
+
+
+# ---- section 8(f) rows: curvature / length objectives, batched finite-difference gradients ------------
+@pytest.mark.parametrize("name", ["buckmore", "clay"])
+def test_curvature_objectives_match_reference(name):
+    """Gamma^2 = path.gamma2(self.s) and path.length of the UNMODIFIED reference (tests/golden/objectives_*,
+    tools/make_golden_objectives.py) against ltk_eval_objectives: a well-conditioned sum of squares, so
+    1e-11 relative (the spline itself differs from FITPACK by ~1e-13 of the peak curvature)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"objectives_{name}_full.npz"))
+    track = ltk.Track(ltk.data_path("tracks", name + ".json"), track_width=float(g["width"]), quiet=True)
+    ev = ltk.LapTimeEvaluator(track, ltk.load_vehicle(ltk.data_path("vehicles", "tbr18.json")), "full", int(g["ns"]))
+    g2, length = ev.curvature_objectives(g["alphas"])
+    assert rel_err(g2, g["gamma2"]).max() <= 1e-11
+    assert rel_err(length, g["length"]).max() <= 1e-14
+    # and against the sample curvatures the profile call returns (same kernel output, summed on the host)
+    pr = ev.profile(g["alphas"][3])
+    assert abs(g2[3] - (np.sum(pr["k"] ** 2) + pr["k"][0] ** 2)) <= 1e-13 * g2[3]
+    ev.close()
+
+
+def test_batched_finite_difference_gradient(golden):
+    """`lap_time_and_gradient` = scipy's 2-point scheme on N + 1 candidates in one batch: every entry must be
+    the difference quotient of two one-at-a-time evaluations."""
+    tj, width, vj, mode = case_setup("buckmore_tbr18_full")
+    track = ltk.Track(tj, track_width=width, quiet=True)
+    traj = ltk.Trajectory(track, ltk.load_vehicle(vj))
+    x = np.random.default_rng(11).uniform(0.05, 1.0, track.size)
+    x[5] = 1.0  # on the upper bound: the step must flip
+    f, grad = traj.lap_time_and_gradient(x)
+    ev = traj.evaluator
+    assert f == ev.lap_times(x)[0]
+    for i in (0, 5, 17, track.size - 1):
+        xi = x.copy()
+        h = -1e-8 if x[i] + 1e-8 > 1.0 else 1e-8
+        xi[i] = x[i] + h
+        assert grad[i] == (ev.lap_times(xi)[0] - f) / (xi[i] - x[i])
+
+
+def test_minimise_curvature_reduces_gamma2():
+    """The curvature optimiser (trajectory.py:60-75) with batched gradients: a few L-BFGS-B iterations must
+    lower Gamma^2 below the centre line's value and leave a feasible line."""
+    track = ltk.Track(ltk.data_path("tracks", "buckmore.json"), track_width=0.8, quiet=True)
+    traj = ltk.Trajectory(track, ltk.load_vehicle(ltk.data_path("vehicles", "tbr18.json")))
+    start = traj.evaluator.curvature_objectives(np.full((1, track.size), 0.5))[0][0]
+    traj.minimise_curvature()
+    end = traj.evaluator.curvature_objectives(np.asarray(traj.alphas)[None, :])[0][0]
+    assert end < 0.8 * start
+    assert np.all(np.asarray(traj.alphas) >= 0.0) and np.all(np.asarray(traj.alphas) <= 1.0)
