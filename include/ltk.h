@@ -96,6 +96,15 @@ int ltk_eval_alphas_timed(ltk_ctx *ctx, const double *d_alphas, int64_t B, doubl
 int ltk_eval_objectives(ltk_ctx *ctx, const double *d_alphas, int64_t B, double *d_gamma2,
                         double *d_length, void *d_workspace, size_t workspace_bytes, void *stream);
 
+/* Candidate generation on the device: d_out[i] = low + (high - low) * u_(first + i), u the stream of
+ * numpy's Generator(Philox(key=[key0, key1])).random() -- so that
+ *     Generator(Philox(key=[key0, key1])).uniform(low, high, n)[first : first + count]
+ * on a host equals the device array bit for bit.  Replaces the per-element np.random.uniform(0, 0.99)
+ * of the population stages (trajectory_bayesian_nonlinear.py:142, :244); ranks generate disjoint
+ * slices of one stream by their `first`. */
+int ltk_random_uniform(int device, uint64_t key0, uint64_t key1, int64_t first, int64_t count, double low,
+                       double high, double *d_out, void *stream);
+
 /* control points -> lap times: the calcMinTime(controls) surface
  * (trajectory_bayesian_nonlinear.py:65-80).  d_xy [B][2][m] row-major with m = n_ctrl + 1 columns
  * (the last column is the closing duplicate and is ignored, exactly as splprep(per=1) overwrites it). */

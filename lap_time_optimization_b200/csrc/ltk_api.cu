@@ -699,6 +699,22 @@ int ltk_topk(ltk_ctx* ctx, const double* d_lap, int64_t B, int64_t index_base, i
                     static_cast<cudaStream_t>(stream));
 }
 
+int ltk_random_uniform(int device, uint64_t key0, uint64_t key1, int64_t first, int64_t count, double low, double high,
+                       double* d_out, void* stream)
+{
+    if (count == 0) return LTK_OK;
+    if (!d_out || first < 0 || count < 0) return fail(nullptr, LTK_E_ARG, "null or negative argument");
+    DeviceGuard guard(device);
+    const long long nblk = (first + count + 3) / 4 - first / 4;
+    long long grid = (nblk + 255) / 256;
+    if (grid > 148 * 16) grid = 148 * 16;
+    philox_uniform<<<(unsigned)grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(key0, key1, first, count, low, high - low, d_out);
+    g_launches.fetch_add(1);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(nullptr, LTK_E_CUDA, "philox_uniform", e);
+    return LTK_OK;
+}
+
 int ltk_path_eval(int device, const double* d_xy, const double* d_knots, int m, const double* d_u, int64_t n,
                   double* d_x, double* d_y, double* d_dx, double* d_dy, double* d_ddx, double* d_ddy,
                   double* d_k_signed, double* d_gamma2, void* stream)

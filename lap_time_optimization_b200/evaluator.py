@@ -147,6 +147,20 @@ class LapTimeEvaluator:
         return {"k1a_spline_solve": float(acc[0]), "k1b_curvature": float(acc[1]), "k2_forward": float(acc[2]),
                 "k3_backward": float(acc[3])}
 
+    def random_population_device(self, count, key, first_row=0, low=0.0, high=0.99):
+        """`count` candidates with every alpha ~ U[low, high) generated ON THE DEVICE (tbn.py:142, :244 draw them
+        one element at a time with np.random.uniform).  `key` = (k0, k1) selects the stream; rows
+        [first_row, first_row + count) of the population
+            np.random.Generator(np.random.Philox(key=key)).uniform(low, high, (total_rows, n_alpha))
+        come out bit for bit, so ranks take disjoint row ranges of one reproducible population."""
+        torch = self.torch
+        out = torch.empty((int(count), self.n_alpha), dtype=torch.float64, device=self.device)
+        rc = self.lib.ltk_random_uniform(self.device.index, int(key[0]), int(key[1]), int(first_row) * self.n_alpha,
+                                         out.numel(), float(low), float(high), _device.ptr(out),
+                                         _device.stream_ptr(torch, self.device))
+        _native.check(rc)
+        return out
+
     def curvature_objectives_device(self, alphas):
         """alphas: float64 CUDA tensor [B, n_alpha] -> (gamma2[B], length[B]) CUDA tensors: the sum of squared
         sample curvatures `Path.gamma2(s)` and `Path.length` of every candidate's spline (the objectives of

@@ -99,6 +99,21 @@ class TrajectoryBayesianNonlinear:
         """`count` candidates with every alpha ~ U[0, 0.99) (tbn.py:142, :244)."""
         return np.random.default_rng(seed).uniform(ALPHA_LOW, ALPHA_HIGH, (count, self.n_alpha))
 
+    def random_population_device(self, count, key, first_row=0):
+        """The same population drawn on the GPU (no host->device copy): rows [first_row, first_row + count) of
+        `np.random.Generator(np.random.Philox(key=key)).uniform(0, 0.99, (rows, n_alpha))`, as a CUDA tensor."""
+        return self.evaluator.random_population_device(count, key, first_row, ALPHA_LOW, ALPHA_HIGH)
+
+    def database(self, count, key, k=DEFAULT_TOPK):
+        """The Bayesian method's training set (tbn.py:136-160: `X_train`, `y_train`) at population scale:
+        `count` device-generated candidates and their lap times, plus the k best.  Returns CUDA tensors
+        (alphas[count, n_alpha], laps[count], best_laps[k], best_idx[k])."""
+        ev = self.evaluator
+        d_a = self.random_population_device(count, key)
+        d_lap = ev.lap_times_device(d_a)
+        best, idx = ev.topk_device(d_lap, k)
+        return d_a, d_lap, best, idx
+
     def population_topk(self, alphas, k=DEFAULT_TOPK):
         """Score a population and keep the k fastest: what `sorted(results)[0:10]` feeds to COBYLA
         (tbn.py:253-257).  Returns (laps[B], best_laps[k], best_indices[k]) as numpy arrays."""

@@ -366,3 +366,20 @@ def test_minimise_curvature_reduces_gamma2():
     end = traj.evaluator.curvature_objectives(np.asarray(traj.alphas)[None, :])[0][0]
     assert end < 0.8 * start
     assert np.all(np.asarray(traj.alphas) >= 0.0) and np.all(np.asarray(traj.alphas) <= 1.0)
+
+
+def test_device_population_equals_numpy_philox(buckmore):
+    """ltk_random_uniform is numpy's Philox4x64-10 stream: a device population equals
+    Generator(Philox(key)).uniform(0, 0.99, ...) bit for bit, for any row offset (rank shards)."""
+    ev, co = buckmore
+    key = (0x0123456789ABCDEF, 42)
+    want = np.random.Generator(np.random.Philox(key=np.array(key, dtype=np.uint64))).uniform(0.0, 0.99, (5000, ev.n_alpha))
+    got = ev.random_population_device(5000, key).cpu().numpy()
+    assert np.array_equal(got, want)
+    for first, count in ((0, 1), (1, 1), (7, 333), (4999, 1), (1234, 3766)):
+        part = ev.random_population_device(count, key, first_row=first).cpu().numpy()
+        assert np.array_equal(part, want[first:first + count])
+    assert got.min() >= 0.0 and got.max() < 0.99
+    # and the database stage on top of it: device-generated candidates, lap times equal to the oracle's
+    laps = ev.lap_times_device(ev.random_population_device(2000, key)).cpu().numpy()
+    assert np.array_equal(laps, co.lap_times(want[:2000]))
