@@ -157,3 +157,25 @@ def test_allgather_topk_gloo_world2():
     expect = sorted(range(1000), key=lambda i: laps_all[i])[:10]
     assert out[0][2] == expect and out[1][2] == expect and out[0][1] == out[1][1]
     assert expect[:2] == [17, 900]
+
+
+def test_result_artefact_writers(tmp_path):
+    """The JSON files of src/__main__.py:196-213 / utils.py:108-136 (what mpc/track.py reads back)."""
+    import json
+    from types import SimpleNamespace
+
+    from lap_time_optimization_b200 import utils
+
+    track = ltk.Track(ltk.data_path("tracks", "buckmore.json"), track_width=0.8, quiet=True)
+    s = np.linspace(0.0, 10.0, 7)
+    path = SimpleNamespace(position=lambda u: np.vstack([np.cos(u), np.sin(u)]))
+    traj = SimpleNamespace(path=path, s=s, velocity=SimpleNamespace(v=np.arange(6.0)))
+    utils.save_result_artefacts(str(tmp_path / "plots" / "nonlinear"), track, traj)
+    d = tmp_path / "plots" / "nonlinear"
+    assert sorted(p.name for p in d.iterdir()) == ["left.json", "path.json", "right.json", "velocities.json", "widths.json"]
+    p = json.load(open(d / "path.json"))
+    assert p["name"] == "path" and p["path"]["x"] == np.cos(s).tolist() and p["path"]["y"] == np.sin(s).tolist()
+    left = json.load(open(d / "left.json"))
+    assert left["path"]["x"] == track.old_left[0].tolist() and len(left["path"]["y"]) == track.old_left.shape[1]
+    assert json.load(open(d / "widths.json"))["width"] == track.widths.tolist()
+    assert json.load(open(d / "velocities.json")) == {"name": "velocities", "velocities": [0.0, 1.0, 2.0, 3.0, 4.0, 5.0]}
