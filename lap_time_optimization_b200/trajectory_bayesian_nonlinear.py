@@ -6,6 +6,7 @@ reference runs one candidate at a time (`Nonlinear`, :239-257; `Bayesian` databa
 from __future__ import annotations
 
 import math
+import time
 
 import numpy as np
 
@@ -122,3 +123,100 @@ class TrajectoryBayesianNonlinear:
         d_lap = ev.lap_times_device(d_a)
         best, idx = ev.topk_device(d_lap, k)
         return d_lap.cpu().numpy(), best.cpu().numpy(), idx.cpu().numpy()
+
+    # -- the --nonlinear stage: random population -> k best -> COBYLA from each (tbn.py:207-270) -------
+    COBYLA_MAXITER = 2000  # tbn.py:219
+
+    def _improvement(self, tau0, tau):
+        return -max(0.0, tau0 - tau)  # tbn.py:211-216
+
+    def optimize_COBYLA(self, args, maxiter=None):
+        """One COBYLA run from (tau0, alpha0) on the reference's objective (tbn.py:207-227): every
+        evaluation is one candidate through the CUDA pipeline.  Returns (tau_star, w_star)."""
+        from scipy.optimize import minimize
+
+        tau0, alpha0 = args
+        bounds = np.array([[ALPHA_LOW, ALPHA_HIGH] for _ in alpha0])
+        ev = self.evaluator
+        res = minimize(lambda x: self._improvement(tau0, ev.lap_times(x)[0]), x0=np.asarray(alpha0, dtype=np.float64),
+                       bounds=bounds, method="COBYLA", options={"maxiter": maxiter or self.COBYLA_MAXITER, "disp": False})
+        return float(ev.lap_times(res.x)[0]), res.x
+
+    def optimize_COBYLA_lockstep(self, starts, maxiter=None):
+        """All COBYLA runs of `Nonlinear()` at once.  The reference maps them over `Pool(processes=1)`, i.e. one
+        after the other (tbn.py:256-260), and most of a run is the optimiser's own host work.  Here every
+        start gets a worker PROCESS that runs scipy's COBYLA and asks this process for each objective
+        value; the requests of all live workers are answered together by ONE batched pipeline call per
+        round.  The workers never touch CUDA (fork is safe for them); results are identical to running
+        `optimize_COBYLA` on each start, because a candidate's lap time does not depend on its batch."""
+        import multiprocessing as mp
+
+        ev = self.evaluator
+        ctx = mp.get_context("fork")
+        maxiter = maxiter or self.COBYLA_MAXITER
+        workers = []
+        for tau0, alpha0 in starts:
+            parent, child = ctx.Pipe()
+            p = ctx.Process(target=_cobyla_worker, args=(child, float(tau0), np.asarray(alpha0, dtype=np.float64), maxiter),
+                            daemon=True)
+            p.start()
+            child.close()
+            workers.append({"conn": parent, "proc": p, "result": None})
+        live = list(range(len(workers)))
+        while live:
+            asks, who = [], []
+            for i in list(live):
+                kind, payload = workers[i]["conn"].recv()
+                if kind == "done":
+                    workers[i]["result"] = payload
+                    live.remove(i)
+                else:
+                    asks.append(payload)
+                    who.append(i)
+            if asks:
+                laps = ev.lap_times(np.vstack(asks))  # one pipeline pass for this round's requests
+                for i, lap in zip(who, laps):
+                    workers[i]["conn"].send(float(lap))
+        out = []
+        for w in workers:
+            w["proc"].join()
+            out.append((float(ev.lap_times(w["result"])[0]), w["result"]))
+        return out
+
+    def Nonlinear(self, population=100, starts=10, key=None, maxiter=None):
+        """Racing line by random search + local refinement (tbn.py:229-270): `population` random candidates
+        scored in one pass, the `starts` fastest refined by COBYLA in lock step, best of everything kept in
+        `self.best` (control points).  `key` selects a device-generated population (Philox stream,
+        `random_population_device`); None draws it on the host with numpy's global generator like the
+        reference.  Returns the run time in seconds."""
+        t0 = time.time()
+        if key is None:
+            alphas = np.random.uniform(ALPHA_LOW, ALPHA_HIGH, (population, self.n_alpha))
+            laps, best, idx = self.population_topk(alphas, starts)
+        else:
+            d_a = self.random_population_device(population, key)
+            laps, best, idx = self.population_topk(d_a, starts)
+            alphas = d_a.cpu().numpy()
+        results = list(zip(laps, alphas))
+        n = min(starts, population)
+        results += self.optimize_COBYLA_lockstep([(best[i], alphas[idx[i]]) for i in range(n)], maxiter)
+        tau_best, alpha_best = sorted(results, key=lambda el: el[0])[0]
+        self.best = self.updateAlphas(alpha_best)
+        self.best_alphas, self.best_tau = np.asarray(alpha_best), float(tau_best)
+        return time.time() - t0
+
+
+def _cobyla_worker(conn, tau0, alpha0, maxiter):
+    """Worker process of `optimize_COBYLA_lockstep`: scipy's COBYLA on the reference's objective
+    (tbn.py:207-227) with the lap time supplied by the parent.  No CUDA in here."""
+    from scipy.optimize import minimize
+
+    def objective(x):
+        conn.send(("ask", np.asarray(x, dtype=np.float64)))
+        tau = conn.recv()
+        return -max(0.0, tau0 - tau)
+
+    bounds = np.array([[ALPHA_LOW, ALPHA_HIGH] for _ in alpha0])
+    res = minimize(objective, x0=alpha0, bounds=bounds, method="COBYLA", options={"maxiter": maxiter, "disp": False})
+    conn.send(("done", np.asarray(res.x, dtype=np.float64)))
+    conn.close()

@@ -383,3 +383,21 @@ def test_device_population_equals_numpy_philox(buckmore):
     # and the database stage on top of it: device-generated candidates, lap times equal to the oracle's
     laps = ev.lap_times_device(ev.random_population_device(2000, key)).cpu().numpy()
     assert np.array_equal(laps, co.lap_times(want[:2000]))
+
+
+def test_lockstep_cobyla_equals_serial_cobyla():
+    """`optimize_COBYLA_lockstep` (worker processes + one batched evaluation per round) must return what
+    `optimize_COBYLA` returns start by start (tbn.py:207-227, :256-260), and `Nonlinear()` keeps the best."""
+    tj, width, vj, mode = case_setup("buckmore_tbr18_bayes")
+    traj = ltk.TrajectoryBayesianNonlinear(ltk.Track(tj, track_width=width, quiet=True), ltk.load_vehicle(vj))
+    a = traj.random_population(64, seed=3)
+    laps, best, idx = traj.population_topk(a, 3)
+    starts = [(best[i], a[idx[i]]) for i in range(3)]
+    lock = traj.optimize_COBYLA_lockstep(starts, maxiter=50)
+    for s, (tau, w) in zip(starts, lock):
+        tau1, w1 = traj.optimize_COBYLA(s, maxiter=50)
+        assert tau == tau1 and np.array_equal(w, w1)  # COBYLA may end on a worse point; Nonlinear() keeps the best overall
+    took = traj.Nonlinear(population=64, starts=2, key=(7, 7), maxiter=50)
+    assert took > 0 and traj.best.shape[0] == 2 and traj.best_tau <= laps.max()
+    want = np.random.Generator(np.random.Philox(key=np.array((7, 7), dtype=np.uint64))).uniform(0, 0.99, (64, traj.n_alpha))
+    assert traj.best_tau <= traj.evaluator.lap_times(want).min()
