@@ -49,6 +49,8 @@ def parse():
     p.add_argument("--ns", type=int, default=None, help="samples per lap incl. end point (default ceil(track length) = 847)")
     p.add_argument("--cpu-sample", type=int, default=2048, help="candidates scored by the CPU baseline")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--sweep-bits", type=int, default=64, choices=[64, 32],
+                   help="32 = the optional fp32 variant of the velocity sweeps (spline and curvature stay fp64)")
     p.add_argument("--lanes", type=int, default=3, help="populations in flight per GPU (1 = strictly one step at a time)")
     return p.parse_args()
 
@@ -206,6 +208,8 @@ def run_ours(args):
     tj, vj = data_paths(args.vehicle)
     track = ltk.Track(tj, track_width=WIDTH, quiet=True)
     ev = ltk.LapTimeEvaluator(track, ltk.load_vehicle(vj), "bayes", args.ns, device=local)
+    if args.sweep_bits == 32:
+        ev.set_sweep_precision(32)
     B, na, ns = args.candidates, ev.n_alpha, ev.ns
     base = rank * B  # global index of this rank's first candidate
     # resident inputs: N_INPUT_SETS distinct populations per rank
@@ -279,11 +283,12 @@ def run_ours(args):
         peak, peak_src = hbm_peak()
         # algorithmic bytes per candidate of each kernel: the shares of A_staged;
         # the K1a -> K1b hand-off (second derivatives, knots) is not in the model and not counted
+        sweep_bytes = 32 * n + 8 if args.sweep_bits == 64 else 24 * n + 8  # fp32 sweeps park 4-byte velocities
         alg = {"k1a_spline_solve": 8 * na, "k1b_curvature": 8 * n, "k2_forward": 16 * n, "k3_backward": 16 * n + 8,
-               "k23_sweep": 32 * n + 8}
+               "k23_sweep": sweep_bytes}
         dom = max(kt, key=lambda k: kt[k])
         achieved = alg[dom] * B / (kt[dom] * 1e-3) / 1e9
-        a_staged = 8 * na + 40 * n + 8
+        a_staged = 8 * na + 8 * n + sweep_bytes  # 8 Na + 40 n + 8 for fp64
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
@@ -294,7 +299,8 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64" if args.sweep_bits == 64 else "f32 sweeps on f64 spline/curvature", "data": "synthetic",
             "config": workload_config(args, na, ns),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * na * 8,

@@ -69,6 +69,12 @@ const char *ltk_last_error(const ltk_ctx *ctx); /* ctx may be NULL: last creatio
 /* Change the sampling density (Trajectory.ns is a plain attribute in the reference). */
 int ltk_set_ns(ltk_ctx *ctx, int ns);
 
+/* Optional fp32 variant of the velocity sweeps (BASELINE.json north_star: 1e-9 for the fp64 kernels,
+ * 1e-4 for an optional fp32 variant): bits = 32 runs velocity.py:14-76 in IEEE fp32 on the fp64
+ * curvature of the spline kernels, lap sum in fp64; bits = 64 (the default) restores the fp64 sweeps.
+ * Affects ltk_eval_alphas / ltk_eval_controls; ltk_profile always uses fp64. */
+int ltk_set_sweep_precision(ltk_ctx *ctx, int bits);
+
 /* Bytes of device scratch ltk_eval_* needs for a batch of B candidates. */
 int ltk_workspace_bytes(const ltk_ctx *ctx, int64_t B, size_t *out_bytes);
 

@@ -20,6 +20,8 @@ struct ltk_ctx {
     double* d_left;  // [2][N]
     double* d_diff;  // [2][N]
     VehDev veh;
+    VehF32 veh32;
+    int sweep_bits;  // 64 (default) or 32: the optional fp32 sweep variant
     // scratch owned by the context
     int4* d_lut;  // engine cell table of the fused sweep (nullptr: none)
     double* d_topk_lap[2];  // ping-pong scratch of the top-k stages, grown on demand
@@ -118,6 +120,28 @@ VehDev make_vehdev(const ltk_vehicle& v)
     }
     if (!engine_nonneg) d.k_span_hi = 0u;  // never take the regular path (it assumes accel >= 0)
     d.lut_shift = 0; d.lut_base = 0; d.lut_top = -1;
+    return d;
+}
+
+VehF32 make_vehf32(const ltk_vehicle& v)
+{
+    VehF32 d;
+    memset(&d, 0, sizeof(d));
+    d.kind = v.kind; d.n_map = v.n_map;
+    d.mass = (float)v.mass; d.mu_g = (float)v.mu_g; d.f_max = (float)v.f_max; d.f_max_sq = (float)v.f_max_sq;
+    d.e0 = (float)v.e0; d.cr2 = (float)v.cr2;
+    for (int i = 0; i < LTK_MAX_ENGINE_MAP; ++i) d.thr[i] = __builtin_inff();
+    if (v.kind == 0) {
+        const int n = v.n_map;
+        for (int i = 0; i < n; ++i) d.thr[i] = (float)v.map_v[i];
+        d.ext_b[0] = (float)v.map_v[0]; d.ext_f[0] = (float)v.map_f[0]; d.ext_s[0] = 0.0f;
+        for (int j = 1; j < n; ++j) {
+            d.ext_b[j] = (float)v.map_v[j - 1];
+            d.ext_f[j] = (float)v.map_f[j - 1];
+            d.ext_s[j] = (float)((v.map_f[j] - v.map_f[j - 1]) / (v.map_v[j] - v.map_v[j - 1]));
+        }
+        d.ext_b[n] = (float)v.map_v[n - 1]; d.ext_f[n] = (float)v.map_f[n - 1]; d.ext_s[n] = 0.0f;
+    }
     return d;
 }
 
@@ -367,6 +391,20 @@ int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m
     if (ev) LTK_CUDA(ctx, cudaEventRecord(ev[2], st));
     if (k1_only) return LTK_OK;
 
+    if (ctx->sweep_bits == 32 && !dumps) {  // optional fp32 sweeps (ltk_sweep_f32.cuh)
+        F32Args f;
+        f.kap = a.kap;
+        f.stage = reinterpret_cast<float*>(ws + w.vacc_off);
+        f.len = a.len; f.lap = d_lap; f.ns = ctx->ns; f.B = B; f.Bp = w.Bp;
+        unsigned g32 = (unsigned)((B + F32_THREADS - 1) / F32_THREADS);
+        if (ctx->veh.kind == 0 && ctx->veh.n_map <= 8) k23_f32<0, 8><<<g32, F32_THREADS, 0, st>>>(f, ctx->veh32);
+        else if (ctx->veh.kind == 0) k23_f32<0, 16><<<g32, F32_THREADS, 0, st>>>(f, ctx->veh32);
+        else k23_f32<1, 8><<<g32, F32_THREADS, 0, st>>>(f, ctx->veh32);
+        if (ev) { LTK_CUDA(ctx, cudaEventRecord(ev[3], st)); LTK_CUDA(ctx, cudaEventRecord(ev[4], st)); }
+        g_launches.fetch_add(1);
+        LTK_CUDA(ctx, cudaGetLastError());
+        return LTK_OK;
+    }
     unsigned grid = (unsigned)((B + SWEEP_THREADS - 1) / SWEEP_THREADS);
     if (ctx->sweep_split && !dumps) {  // separate forward / backward kernels (A/B reference for the fused one)
         SweepArgs s;
@@ -494,6 +532,8 @@ int ltk_create(ltk_ctx** out, int device, const double* h_left_xy, const double*
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
     ctx->veh = make_vehdev(*vehicle);
+    ctx->veh32 = make_vehf32(*vehicle);
+    ctx->sweep_bits = 64;
     ctx->k1_g_override = 0;
     ctx->k1_staged_override = -1;
     if (const char* s = getenv("LTK_K1_G")) ctx->k1_g_override = atoi(s);
@@ -562,6 +602,14 @@ int ltk_set_ns(ltk_ctx* ctx, int ns)
         ctx->ns = old;
         return fail(ctx, LTK_E_UNSUPPORTED, "no K1 configuration fits shared memory");
     }
+    return LTK_OK;
+}
+
+int ltk_set_sweep_precision(ltk_ctx* ctx, int bits)
+{
+    if (!ctx) return LTK_E_ARG;
+    if (bits != 64 && bits != 32) return fail(ctx, LTK_E_ARG, "sweep precision must be 64 or 32");
+    ctx->sweep_bits = bits;
     return LTK_OK;
 }
 

@@ -68,6 +68,14 @@ class LapTimeEvaluator:
         _native.check(self.lib.ltk_set_ns(self._ctx, int(ns)), self._ctx)
         self.ns = int(ns)
 
+    def set_sweep_precision(self, bits):
+        """64 (default): everything in fp64.  32: the optional fp32 variant of the velocity sweeps (spline and
+        curvature stay fp64; lap times then agree with the fp64 ones to ~1e-5, tolerance 1e-4)."""
+        _native.check(self.lib.ltk_set_sweep_precision(self._ctx, int(bits)), self._ctx)
+        for lane in (getattr(self, "_lanes", None) or [])[1:]:
+            lane.ev.set_sweep_precision(bits)
+        self.sweep_bits = int(bits)
+
     # -- lanes: several populations in flight ---------------------------------------------------------
     def lanes(self, n=3):
         """`n` independent (evaluator, stream) pairs for scoring several populations CONCURRENTLY.
@@ -84,6 +92,8 @@ class LapTimeEvaluator:
         while len(cur) < n:
             ev = self if not cur else LapTimeEvaluator(self.track, self.vehicle, self.mode, self.ns, self.device.index,
                                                        self.max_workspace_bytes)
+            if cur and getattr(self, "sweep_bits", 64) != 64:
+                ev.set_sweep_precision(self.sweep_bits)
             cur.append(Lane(ev, torch.cuda.Stream(self.device)))
         self._lanes = cur
         return cur[:n]

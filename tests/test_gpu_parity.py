@@ -401,3 +401,20 @@ def test_lockstep_cobyla_equals_serial_cobyla():
     assert took > 0 and traj.best.shape[0] == 2 and traj.best_tau <= laps.max()
     want = np.random.Generator(np.random.Philox(key=np.array((7, 7), dtype=np.uint64))).uniform(0, 0.99, (64, traj.n_alpha))
     assert traj.best_tau <= traj.evaluator.lap_times(want).min()
+
+
+@pytest.mark.parametrize("name", ["buckmore_tbr18_bayes", "buckmore_mx5_bayes"])
+def test_fp32_sweep_variant(name):
+    """The optional fp32 variant of the sweeps (north_star tolerance 1e-4): against the fp64 kernels on 65,536
+    candidates and against the reference's golden lap times."""
+    ev, co = make(name)
+    a = np.random.default_rng(32).uniform(0.0, 0.99, (65536, ev.n_alpha))
+    l64 = ev.lap_times(a)
+    ev.set_sweep_precision(32)
+    l32 = ev.lap_times(a)
+    rel = rel_err(l32, l64)
+    print(f"fp32 sweeps vs fp64 ({name}): median {np.median(rel):.2e}, p99 {np.percentile(rel, 99):.2e}, max {rel.max():.2e}")
+    assert rel.max() <= 1e-4 and np.median(rel) <= 2e-5
+    ev.set_sweep_precision(64)
+    assert np.array_equal(ev.lap_times(a), l64)
+    ev.close()
