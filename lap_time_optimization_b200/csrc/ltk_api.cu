@@ -27,6 +27,7 @@ struct ltk_ctx {
     double* d_topk_lap[2];  // ping-pong scratch of the top-k stages, grown on demand
     long long* d_topk_idx[2];
     long long topk_cap;     // entries per scratch buffer
+    unsigned* d_ticket;     // "last block finishes" counter of the single-launch top-k
     void* d_profile_ws;
     size_t profile_ws_bytes;
     int k1_g_override, k1_staged_override, k1_threads_override, sweep_split, sweep_mode, k1_mode;
@@ -296,8 +297,8 @@ bool pick_k1f(const ltk_ctx* ctx, K1FConfig* out)
 {
     if (ctx->k1_mode == 1) return false;  // LTK_K1=old: the previous K1a + K1b pair (A/B reference)
     if (k1a_smem_bytes(ctx->N) > ctx->smem_optin) return false;
-    const int cand[3][2] = {{4, 256}, {4, 128}, {8, 256}};  // measured order (0.305 / 0.318 / 0.381 ms)
-    for (int i = 0; i < 3; ++i) {
+    const int cand[5][2] = {{4, 256}, {4, 128}, {8, 256}, {2, 128}, {2, 64}};  // measured order (0.305 / 0.318 / 0.381 ms)
+    for (int i = 0; i < 5; ++i) {
         int G = cand[i][0], T = cand[i][1];
         if (ctx->k1_g_override > 0 && G != ctx->k1_g_override) continue;
         if (ctx->k1_threads_override > 0 && T != ctx->k1_threads_override) continue;
@@ -319,6 +320,8 @@ cudaError_t launch_k1f(const K1Args& a, size_t smem, cudaStream_t st)
 
 cudaError_t launch_k1f_cfg(const K1FConfig& c, const K1Args& a, cudaStream_t st)
 {
+    if (c.G == 2 && c.threads == 128) return launch_k1f<2, 128, 8>(a, c.smem, st);
+    if (c.G == 2) return launch_k1f<2, 64, 12>(a, c.smem, st);
     if (c.G == 4 && c.threads == 128) return launch_k1f<4, 128, 5>(a, c.smem, st);
     if (c.G == 4) return launch_k1f<4, 256, 4>(a, c.smem, st);
     return launch_k1f<8, 256, 2>(a, c.smem, st);
@@ -461,7 +464,8 @@ int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m
     return LTK_OK;
 }
 
-// stages of topk_select until a single block writes the caller's buffers
+// top-k of `count` keys.  Up to TOPK_BLOCK_KEYS / k blocks: ONE launch (the block that finishes last
+// merges every block's winners); beyond that, stages chained until few enough blocks are left.
 int run_topk(ltk_ctx* ctx, const double* d_lap, const long long* d_idx, long long count, long long index_base, int k,
              double* d_best_lap, long long* d_best_idx, cudaStream_t st)
 {
@@ -481,15 +485,22 @@ int run_topk(ltk_ctx* ctx, const double* d_lap, const long long* d_idx, long lon
         }
         ctx->topk_cap = cap;
     }
+    if (blocks > 1 && !ctx->d_ticket) {
+        LTK_CUDA(ctx, cudaMalloc(&ctx->d_ticket, sizeof(unsigned)));
+        LTK_CUDA(ctx, cudaMemsetAsync(ctx->d_ticket, 0, sizeof(unsigned), st));
+    }
     int pp = 0;
     while (true) {
-        const bool last = (blocks == 1);
-        double* o_lap = last ? d_best_lap : ctx->d_topk_lap[pp];
-        long long* o_idx = last ? d_best_idx : ctx->d_topk_idx[pp];
-        topk_select<<<(unsigned)blocks, TOPK_THREADS, 0, st>>>(d_lap, d_idx, count, index_base, k, o_lap, o_idx);
+        const bool single = (blocks == 1);
+        const bool fused = !single && blocks * k <= TOPK_BLOCK_KEYS;  // last block merges in the same launch
+        double* o_lap = (single || fused) ? d_best_lap : ctx->d_topk_lap[pp];
+        long long* o_idx = (single || fused) ? d_best_idx : ctx->d_topk_idx[pp];
+        topk_select<<<(unsigned)blocks, TOPK_THREADS, 0, st>>>(d_lap, d_idx, count, index_base, k, o_lap, o_idx,
+                                                               ctx->d_topk_lap[pp], ctx->d_topk_idx[pp],
+                                                               fused ? ctx->d_ticket : nullptr);
         g_launches.fetch_add(1);
         LTK_CUDA(ctx, cudaGetLastError());
-        if (last) break;
+        if (single || fused) break;
         d_lap = o_lap; d_idx = o_idx; count = blocks * k; index_base = 0;
         blocks = (count + TOPK_BLOCK_KEYS - 1) / TOPK_BLOCK_KEYS;
         pp ^= 1;
@@ -549,7 +560,7 @@ int ltk_create(ltk_ctx** out, int device, const double* h_left_xy, const double*
     ctx->k1_threads_override = 0;
     if (const char* s = getenv("LTK_K1_THREADS")) {
         int t = atoi(s);
-        if (t == 128 || t == 256 || t == 512 || t == 1024) ctx->k1_threads_override = t;
+        if (t == 64 || t == 128 || t == 256 || t == 512 || t == 1024) ctx->k1_threads_override = t;
     }
     int4 lut_cells[LTK_LUT_MAX_CELLS];
     const int n_cells = getenv("LTK_NO_ENGINE_LUT") ? 0 : build_engine_lut(*vehicle, &ctx->veh, lut_cells);
@@ -570,7 +581,8 @@ int ltk_create(ltk_ctx** out, int device, const double* h_left_xy, const double*
         return LTK_E_CUDA;
     }
     K1Config cfg;
-    if (!pick_k1(ctx, &cfg)) {
+    K1FConfig fcfg0;
+    if (!pick_k1f(ctx, &fcfg0) && !pick_k1(ctx, &cfg)) {
         fail(nullptr, LTK_E_UNSUPPORTED, "control-point count too large for shared memory");
         ltk_destroy(ctx);
         return LTK_E_UNSUPPORTED;
@@ -587,6 +599,7 @@ void ltk_destroy(ltk_ctx* ctx)
     cudaFree(ctx->d_diff);
     cudaFree(ctx->d_lut);
     for (int i = 0; i < 2; ++i) { cudaFree(ctx->d_topk_lap[i]); cudaFree(ctx->d_topk_idx[i]); }
+    cudaFree(ctx->d_ticket);
     cudaFree(ctx->d_profile_ws);
     delete ctx;
 }
@@ -598,7 +611,8 @@ int ltk_set_ns(ltk_ctx* ctx, int ns)
     int old = ctx->ns;
     ctx->ns = ns;
     K1Config cfg;
-    if (!pick_k1(ctx, &cfg)) {
+    K1FConfig fcfg0;
+    if (!pick_k1f(ctx, &fcfg0) && !pick_k1(ctx, &cfg)) {
         ctx->ns = old;
         return fail(ctx, LTK_E_UNSUPPORTED, "no K1 configuration fits shared memory");
     }

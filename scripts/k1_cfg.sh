@@ -1,6 +1,5 @@
-# K1 configuration sweep (G candidates per CTA, T threads of K1b); prints step and per-kernel times
-run() { python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null > /tmp/o.json; python -c "import json; d=json.load(open('/tmp/o.json')); print('$1', round(d['ms_per_step'],4), d['roofline']['kernel_ms'])"; }
-run "K1 default"
-LTK_K1_THREADS=256 run "K1b T=256 (G=4)"
-LTK_K1_G=8 LTK_K1_THREADS=256 run "K1b G=8 T=256"
-LTK_K1=old run "K1 old pair"
+# K1b configuration sweep (G candidates per CTA, T threads); prints step and per-kernel times (one population at a time)
+run() { python bench.py --steps 20 --warmup 3 --no-cpu-baseline --lanes 1 2>/dev/null > /tmp/o.json; python -c "import json; d=json.load(open('/tmp/o.json')); print('$1', round(d['ms_per_step'],4), d['roofline']['kernel_ms'])"; }
+LTK_K1_G=4 LTK_K1_THREADS=256 run "K1b G=4 T=256"
+LTK_K1_G=2 LTK_K1_THREADS=128 run "K1b G=2 T=128"
+LTK_K1_G=2 LTK_K1_THREADS=64 run "K1b G=2 T=64"
