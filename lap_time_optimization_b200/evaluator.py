@@ -67,6 +67,8 @@ class LapTimeEvaluator:
         """`Trajectory.ns` is a plain attribute in the reference; changing it re-samples the lap."""
         _native.check(self.lib.ltk_set_ns(self._ctx, int(ns)), self._ctx)
         self.ns = int(ns)
+        for lane in (getattr(self, "_lanes", None) or [])[1:]:
+            lane.ev.set_ns(ns)
 
     def set_sweep_precision(self, bits):
         """64 (default): everything in fp64.  32: the optional fp32 variant of the velocity sweeps (spline and

@@ -418,3 +418,20 @@ def test_fp32_sweep_variant(name):
     ev.set_sweep_precision(64)
     assert np.array_equal(ev.lap_times(a), l64)
     ev.close()
+
+
+def test_ns_change_reaches_every_lane(golden):
+    """`Trajectory.ns` is a plain attribute (trajectory.py:35): after a change, populations large enough to be
+    spread over the lanes must be sampled at the new density on every lane."""
+    g = golden("buckmore_tbr18_bayes_ns2501")
+    ev, co = make("buckmore_tbr18_bayes")
+    a = np.random.default_rng(8).uniform(0.0, 0.99, (3 * 65536 + 17, ev.n_alpha))
+    first = ev.lap_times(a)  # creates the lanes at ns = 847
+    assert np.array_equal(first[:4096], co.lap_times(a[:4096]))
+    ev.set_ns(int(g["ns"]))
+    co2 = c_oracle.COracle(OracleTrack(*case_setup("buckmore_tbr18_bayes")[:2]), load_vehicle(case_setup("buckmore_tbr18_bayes")[2]),
+                           "bayes", int(g["ns"]), device_sum_order=True)
+    second = ev.lap_times(a)
+    for lo in (0, 65536, 2 * 65536, 3 * 65536):  # one slice per lane / chunk
+        assert np.array_equal(second[lo:lo + 17], co2.lap_times(a[lo:lo + 17]))
+    ev.close()
