@@ -75,6 +75,13 @@ int ltk_set_ns(ltk_ctx *ctx, int ns);
  * Affects ltk_eval_alphas / ltk_eval_controls; ltk_profile always uses fp64. */
 int ltk_set_sweep_precision(ltk_ctx *ctx, int bits);
 
+/* Scheduling knob, no effect on results.  on (default): a population that fills the sweep kernel's warp
+ * slots unevenly (65,536 candidates = 3.46 warps per scheduler) is split -- whole layers of one warp per
+ * scheduler to the two-chain kernel, the remainder to the one-chain kernel on a second stream of the
+ * context (0.527 -> 0.487 ms).  off: one sweep launch; callers that keep several populations in flight
+ * on different contexts switch it off (the extra concurrent kernel costs more than it gains there). */
+int ltk_set_sweep_split(ltk_ctx *ctx, int on);
+
 /* Bytes of device scratch ltk_eval_* needs for a batch of B candidates. */
 int ltk_workspace_bytes(const ltk_ctx *ctx, int64_t B, size_t *out_bytes);
 

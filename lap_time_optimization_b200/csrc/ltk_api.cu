@@ -28,6 +28,9 @@ struct ltk_ctx {
     long long* d_topk_idx[2];
     long long topk_cap;     // entries per scratch buffer
     unsigned* d_ticket;     // "last block finishes" counter of the single-launch top-k
+    cudaStream_t aux_stream;  // the remainder sweep (see run_pipeline) runs next to the main one
+    cudaEvent_t aux_ev[2];
+    int sweep_remainder;      // 0 disables the split (LTK_SWEEP_REMAINDER=0)
     void* d_profile_ws;
     size_t profile_ws_bytes;
     int k1_g_override, k1_staged_override, k1_threads_override, sweep_split, sweep_mode, k1_mode;
@@ -297,8 +300,8 @@ bool pick_k1f(const ltk_ctx* ctx, K1FConfig* out)
 {
     if (ctx->k1_mode == 1) return false;  // LTK_K1=old: the previous K1a + K1b pair (A/B reference)
     if (k1a_smem_bytes(ctx->N) > ctx->smem_optin) return false;
-    const int cand[5][2] = {{4, 256}, {4, 128}, {8, 256}, {2, 128}, {2, 64}};  // measured order (0.305 / 0.318 / 0.381 ms)
-    for (int i = 0; i < 5; ++i) {
+    const int cand[7][2] = {{4, 256}, {4, 128}, {8, 256}, {2, 128}, {2, 64}, {1, 256}, {1, 128}};  // measured order
+    for (int i = 0; i < 7; ++i) {
         int G = cand[i][0], T = cand[i][1];
         if (ctx->k1_g_override > 0 && G != ctx->k1_g_override) continue;
         if (ctx->k1_threads_override > 0 && T != ctx->k1_threads_override) continue;
@@ -320,6 +323,8 @@ cudaError_t launch_k1f(const K1Args& a, size_t smem, cudaStream_t st)
 
 cudaError_t launch_k1f_cfg(const K1FConfig& c, const K1Args& a, cudaStream_t st)
 {
+    if (c.G == 1 && c.threads == 256) return launch_k1f<1, 256, 2>(a, c.smem, st);
+    if (c.G == 1) return launch_k1f<1, 128, 4>(a, c.smem, st);
     if (c.G == 2 && c.threads == 128) return launch_k1f<2, 128, 8>(a, c.smem, st);
     if (c.G == 2) return launch_k1f<2, 64, 12>(a, c.smem, st);
     if (c.G == 4 && c.threads == 128) return launch_k1f<4, 128, 5>(a, c.smem, st);
@@ -429,7 +434,7 @@ int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m
         g_launches.fetch_add(2);
     } else {
         FusedArgs f;
-        f.lut = ctx->d_lut; f.Bp = w.Bp;
+        f.lut = ctx->d_lut; f.Bp = w.Bp; f.first = 0; f.last = w.Bp;
         f.kap = a.kap;
         f.stage = reinterpret_cast<double*>(ws + w.vacc_off);
         f.rot = a.rot; f.len = a.len; f.lap = d_lap;
@@ -442,6 +447,33 @@ int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m
         // Small batches are latency-bound: one chain per thread, two warps per 32 candidates (K23r).
         // From one resident wave upwards the two-chains-per-thread kernel is as fast or faster.
         const bool roles = (ctx->sweep_mode == 2) || (ctx->sweep_mode == 0 && !dumps && B <= 16384);
+        // A population that fills the two-chain kernel's warp slots unevenly -- e.g. 65,536 candidates =
+        // 3.46 warps per scheduler, so most schedulers carry 4 warps and the rest idle a quarter of the
+        // time -- is split: whole layers of one warp per scheduler go to the two-chain kernel, the
+        // remainder to the one-chain kernel (half-size warps, two per 32 candidates) on a second stream,
+        // so that the busiest schedulers carry 3.5 warps' worth instead of 4.
+        const long long layer = 32LL * 4 * ctx->sm_count;  // candidates in one warp per scheduler
+        const long long whole = (w.Bp / layer) * layer;
+        const long long rest = w.Bp - whole;
+        const bool split = !roles && !dumps && ctx->sweep_mode == 0 && ctx->sweep_remainder && ctx->aux_stream &&
+                           whole > 0 && rest > 0 && 2 * rest <= layer + layer / 8;
+        if (split) {
+            f.first = whole; f.last = w.Bp;
+            LTK_CUDA(ctx, cudaEventRecord(ctx->aux_ev[0], st));
+            LTK_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_ev[0], 0));
+            unsigned gr = (unsigned)(rest / 32);
+            if (ctx->veh.kind == 0) {
+                if (ctx->veh.lut_top >= 0) k23_roles<0, 0><<<gr, ROLES_THREADS, 0, ctx->aux_stream>>>(f, ctx->veh);
+                else if (ctx->veh.n_map <= 8) k23_roles<0, 8><<<gr, ROLES_THREADS, 0, ctx->aux_stream>>>(f, ctx->veh);
+                else k23_roles<0, 16><<<gr, ROLES_THREADS, 0, ctx->aux_stream>>>(f, ctx->veh);
+            } else {
+                k23_roles<1, 8><<<gr, ROLES_THREADS, 0, ctx->aux_stream>>>(f, ctx->veh);
+            }
+            g_launches.fetch_add(1);
+            LTK_CUDA(ctx, cudaEventRecord(ctx->aux_ev[1], ctx->aux_stream));
+            f.first = 0; f.last = whole;
+            gridf = (unsigned)(whole / FUSED_THREADS);
+        }
         if (roles) {
             if (ctx->veh.kind == 0) {
                 if (ctx->veh.lut_top >= 0) k23_roles<0, 0><<<gridr, ROLES_THREADS, 0, st>>>(f, ctx->veh);
@@ -457,6 +489,7 @@ int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m
         } else {
             k23_sweep<1, 8><<<gridf, FUSED_THREADS, 0, st>>>(f, ctx->veh);
         }
+        if (split) LTK_CUDA(ctx, cudaStreamWaitEvent(st, ctx->aux_ev[1], 0));
         if (ev) { LTK_CUDA(ctx, cudaEventRecord(ev[3], st)); LTK_CUDA(ctx, cudaEventRecord(ev[4], st)); }
         g_launches.fetch_add(1);
     }
@@ -580,6 +613,13 @@ int ltk_create(ltk_ctx** out, int device, const double* h_left_xy, const double*
         ltk_destroy(ctx);
         return LTK_E_CUDA;
     }
+    ctx->sweep_remainder = 1;
+    if (const char* s = getenv("LTK_SWEEP_REMAINDER")) ctx->sweep_remainder = atoi(s);
+    if (cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) != cudaSuccess) ctx->aux_stream = nullptr;
+    if (ctx->aux_stream) {
+        cudaEventCreateWithFlags(&ctx->aux_ev[0], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->aux_ev[1], cudaEventDisableTiming);
+    }
     K1Config cfg;
     K1FConfig fcfg0;
     if (!pick_k1f(ctx, &fcfg0) && !pick_k1(ctx, &cfg)) {
@@ -600,6 +640,7 @@ void ltk_destroy(ltk_ctx* ctx)
     cudaFree(ctx->d_lut);
     for (int i = 0; i < 2; ++i) { cudaFree(ctx->d_topk_lap[i]); cudaFree(ctx->d_topk_idx[i]); }
     cudaFree(ctx->d_ticket);
+    if (ctx->aux_stream) { cudaStreamDestroy(ctx->aux_stream); cudaEventDestroy(ctx->aux_ev[0]); cudaEventDestroy(ctx->aux_ev[1]); }
     cudaFree(ctx->d_profile_ws);
     delete ctx;
 }
@@ -624,6 +665,13 @@ int ltk_set_sweep_precision(ltk_ctx* ctx, int bits)
     if (!ctx) return LTK_E_ARG;
     if (bits != 64 && bits != 32) return fail(ctx, LTK_E_ARG, "sweep precision must be 64 or 32");
     ctx->sweep_bits = bits;
+    return LTK_OK;
+}
+
+int ltk_set_sweep_split(ltk_ctx* ctx, int on)
+{
+    if (!ctx) return LTK_E_ARG;
+    ctx->sweep_remainder = on ? 1 : 0;
     return LTK_OK;
 }
 

@@ -48,6 +48,7 @@ struct FusedArgs {
     const int4* lut;    // engine cell table (EngineLut), device memory; nullptr when ENG != 0
     int ns;
     long long B, Bp;
+    long long first, last;  // candidates [first, last) of the padded population are this launch's (multiples of 32)
 };
 
 // ---- engine map by cell table ---------------------------------------------------------------------
@@ -252,8 +253,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 8) k23_sweep(FusedArgs a, VehDe
             for (int i = threadIdx.x; i <= V.lut_top; i += FUSED_THREADS) S.cell[i] = a.lut[i];
         __syncthreads();
     }
-    const long long b_raw = (long long)blockIdx.x * FUSED_THREADS + threadIdx.x;
-    if (b_raw - (threadIdx.x & 31) >= a.Bp) return;  // whole warp beyond the padded population
+    const long long b_raw = a.first + (long long)blockIdx.x * FUSED_THREADS + threadIdx.x;
+    if (b_raw - (threadIdx.x & 31) >= a.last) return;  // whole warp beyond this launch's candidates
     // lanes in [B, Bp) sweep the padding copies K1 wrote (so that warp votes see a full warp)
     const long long b = b_raw;
     const int n = a.ns - 1;

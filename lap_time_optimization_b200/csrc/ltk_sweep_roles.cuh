@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(ROLES_THREADS, 14) k23_roles(FusedArgs a, VehD
     }
     const int role = threadIdx.x >> 5, lane = threadIdx.x & 31;  // warp 0 forward, warp 1 backward
     // one CTA per 32 candidates of the padded population (lanes in [B, Bp) sweep K1's padding copies)
-    const long long b = (long long)blockIdx.x * 32 + lane;
+    const long long b = a.first + (long long)blockIdx.x * 32 + lane;
     const int n = a.ns - 1;
     const size_t base = tile_base(b, n);
     const int p = a.rot[b];

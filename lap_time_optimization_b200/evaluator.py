@@ -98,6 +98,9 @@ class LapTimeEvaluator:
                 ev.set_sweep_precision(self.sweep_bits)
             cur.append(Lane(ev, torch.cuda.Stream(self.device)))
         self._lanes = cur
+        if n > 1:  # several populations in flight: one sweep launch each (see ltk_set_sweep_split)
+            for lane in cur:
+                _native.check(self.lib.ltk_set_sweep_split(lane.ev._ctx, 0), lane.ev._ctx)
         return cur[:n]
 
     # -- sizing -----------------------------------------------------------------------------------
