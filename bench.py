@@ -284,8 +284,7 @@ def run_ours(args):
         # algorithmic bytes per candidate of each kernel: the shares of A_staged;
         # the K1a -> K1b hand-off (second derivatives, knots) is not in the model and not counted
         sweep_bytes = 32 * n + 8 if args.sweep_bits == 64 else 24 * n + 8  # fp32 sweeps park 4-byte velocities
-        alg = {"k1a_spline_solve": 8 * na, "k1b_curvature": 8 * n, "k2_forward": 16 * n, "k3_backward": 16 * n + 8,
-               "k23_sweep": sweep_bytes}
+        alg = {"k1a_spline_solve": 8 * na, "k1b_curvature": 8 * n, "k23_sweep": sweep_bytes}
         dom = max(kt, key=lambda k: kt[k])
         achieved = alg[dom] * B / (kt[dom] * 1e-3) / 1e9
         a_staged = 8 * na + 8 * n + sweep_bytes  # 8 Na + 40 n + 8 for fp64

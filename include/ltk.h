@@ -97,8 +97,7 @@ int ltk_eval_alphas(ltk_ctx *ctx, const double *d_alphas, int64_t B, double *d_l
                     void *d_workspace, size_t workspace_bytes, void *stream);
 
 /* Measurement hook: same work as ltk_eval_alphas, with CUDA events recorded on `stream` around each
- * kernel; synchronises and writes the durations in milliseconds to h_ms[4] = {K1a, K1b, K23, -1}
- * ({K1a, K1b, K2, K3} when the sweeps run as two kernels, LTK_SWEEP=split). */
+ * kernel; synchronises and writes the durations in milliseconds to h_ms[4] = {K1a, K1b, K23, -1}. */
 int ltk_eval_alphas_timed(ltk_ctx *ctx, const double *d_alphas, int64_t B, double *d_lap,
                           void *d_workspace, size_t workspace_bytes, void *stream, float *h_ms);
 

@@ -33,7 +33,7 @@ struct ltk_ctx {
     int sweep_remainder;      // 0 disables the split (LTK_SWEEP_REMAINDER=0)
     void* d_profile_ws;
     size_t profile_ws_bytes;
-    int k1_g_override, k1_staged_override, k1_threads_override, sweep_split, sweep_mode, k1_mode;
+    int k1_g_override, k1_staged_override, k1_threads_override, sweep_mode, k1_mode;
     char err[256];
 };
 
@@ -413,26 +413,7 @@ int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m
         LTK_CUDA(ctx, cudaGetLastError());
         return LTK_OK;
     }
-    unsigned grid = (unsigned)((B + SWEEP_THREADS - 1) / SWEEP_THREADS);
-    if (ctx->sweep_split && !dumps) {  // separate forward / backward kernels (A/B reference for the fused one)
-        SweepArgs s;
-        s.kap = a.kap;
-        s.vacc = reinterpret_cast<double*>(ws + w.vacc_off);
-        s.rot = a.rot; s.len = a.len; s.lap = d_lap;
-        s.vdec = nullptr; s.vmin = nullptr;
-        s.ns = ctx->ns; s.B = B; s.Bp = w.Bp;
-        if (ctx->veh.kind == 0) {
-            if (ctx->veh.n_map <= 8) k2_forward<0, 8><<<grid, SWEEP_THREADS, 0, st>>>(s, ctx->veh);
-            else k2_forward<0, 16><<<grid, SWEEP_THREADS, 0, st>>>(s, ctx->veh);
-        } else {
-            k2_forward<1, 8><<<grid, SWEEP_THREADS, 0, st>>>(s, ctx->veh);
-        }
-        if (ev) LTK_CUDA(ctx, cudaEventRecord(ev[3], st));
-        if (ctx->veh.kind == 0) k3_backward<0><<<grid, SWEEP_THREADS, 0, st>>>(s, ctx->veh);
-        else k3_backward<1><<<grid, SWEEP_THREADS, 0, st>>>(s, ctx->veh);
-        if (ev) LTK_CUDA(ctx, cudaEventRecord(ev[4], st));
-        g_launches.fetch_add(2);
-    } else {
+    {
         FusedArgs f;
         f.lut = ctx->d_lut; f.Bp = w.Bp; f.first = 0; f.last = w.Bp;
         f.kap = a.kap;
@@ -582,12 +563,10 @@ int ltk_create(ltk_ctx** out, int device, const double* h_left_xy, const double*
     ctx->k1_staged_override = -1;
     if (const char* s = getenv("LTK_K1_G")) ctx->k1_g_override = atoi(s);
     if (const char* s = getenv("LTK_K1_STAGED")) ctx->k1_staged_override = atoi(s);
-    ctx->sweep_split = 0;
     ctx->k1_mode = 0;
     if (const char* s = getenv("LTK_K1")) ctx->k1_mode = (strcmp(s, "old") == 0) ? 1 : 0;
     ctx->sweep_mode = 0;
     if (const char* s = getenv("LTK_SWEEP")) {
-        ctx->sweep_split = (strcmp(s, "split") == 0);
         ctx->sweep_mode = (strcmp(s, "fused") == 0) ? 1 : (strcmp(s, "roles") == 0) ? 2 : 0;
     }
     ctx->k1_threads_override = 0;
@@ -711,7 +690,7 @@ int ltk_eval_alphas_timed(ltk_ctx* ctx, const double* d_alphas, int64_t B, doubl
         cudaError_t e = cudaEventSynchronize(ev[4]);
         for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventElapsedTime(&h_ms[i], ev[i], ev[i + 1]);
         if (e != cudaSuccess) rc = fail(ctx, LTK_E_CUDA, "event timing", e);
-        if (!ctx->sweep_split) h_ms[3] = -1.0f;  // one sweep kernel: no separate backward launch
+        h_ms[3] = -1.0f;  // one sweep kernel: no separate backward launch
     }
     for (int i = 0; i < 5; ++i) cudaEventDestroy(ev[i]);
     return rc;

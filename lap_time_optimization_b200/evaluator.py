@@ -192,10 +192,7 @@ class LapTimeEvaluator:
             _native.check(rc, self._ctx)
             acc += np.array(ms[:])
         acc /= reps
-        if acc[3] < 0:  # one sweep kernel (forward and backward chains together; the default)
-            return {"k1a_spline_solve": float(acc[0]), "k1b_curvature": float(acc[1]), "k23_sweep": float(acc[2])}
-        return {"k1a_spline_solve": float(acc[0]), "k1b_curvature": float(acc[1]), "k2_forward": float(acc[2]),
-                "k3_backward": float(acc[3])}
+        return {"k1a_spline_solve": float(acc[0]), "k1b_curvature": float(acc[1]), "k23_sweep": float(acc[2])}
 
     def random_population_device(self, count, key, first_row=0, low=0.0, high=0.99):
         """`count` candidates with every alpha ~ U[low, high) generated ON THE DEVICE (tbn.py:142, :244 draw them
