@@ -147,12 +147,13 @@ class TrajectoryBayesianNonlinear:
         after the other (tbn.py:256-260), and most of a run is the optimiser's own host work.  Here every
         start gets a worker PROCESS that runs scipy's COBYLA and asks this process for each objective
         value; the requests of all live workers are answered together by ONE batched pipeline call per
-        round.  The workers never touch CUDA (fork is safe for them); results are identical to running
+        round.  The workers never touch CUDA and are spawned, not forked (this process has CUDA and NCCL
+        threads; importing the package needs neither torch nor a GPU); results are identical to running
         `optimize_COBYLA` on each start, because a candidate's lap time does not depend on its batch."""
         import multiprocessing as mp
 
         ev = self.evaluator
-        ctx = mp.get_context("fork")
+        ctx = mp.get_context("spawn")
         maxiter = maxiter or self.COBYLA_MAXITER
         workers = []
         for tau0, alpha0 in starts:
