@@ -147,42 +147,49 @@ class TrajectoryBayesianNonlinear:
         after the other (tbn.py:256-260), and most of a run is the optimiser's own host work.  Here every
         start gets a worker PROCESS that runs scipy's COBYLA and asks this process for each objective
         value; the requests of all live workers are answered together by ONE batched pipeline call per
-        round.  The workers never touch CUDA and are spawned, not forked (this process has CUDA and NCCL
-        threads; importing the package needs neither torch nor a GPU); results are identical to running
-        `optimize_COBYLA` on each start, because a candidate's lap time does not depend on its batch."""
-        import multiprocessing as mp
+        round.  The workers are plain subprocesses (`_cobyla_worker.py`: no CUDA, no torch, no fork from
+        this multi-threaded process, no dependence on the caller's `__main__`); results are identical to
+        running `optimize_COBYLA` on each start, because a candidate's lap time does not depend on its batch."""
+        import os
+        import pickle
+        import subprocess
+        import sys
 
         ev = self.evaluator
-        ctx = mp.get_context("spawn")
         maxiter = maxiter or self.COBYLA_MAXITER
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
         workers = []
         for tau0, alpha0 in starts:
-            parent, child = ctx.Pipe()
-            p = ctx.Process(target=_cobyla_worker, args=(child, float(tau0), np.asarray(alpha0, dtype=np.float64), maxiter),
-                            daemon=True)
-            p.start()
-            child.close()
-            workers.append({"conn": parent, "proc": p, "result": None})
+            p = subprocess.Popen([sys.executable, "-m", "lap_time_optimization_b200._cobyla_worker"], stdin=subprocess.PIPE,
+                                 stdout=subprocess.PIPE, env=env)
+            pickle.dump((float(tau0), np.asarray(alpha0, dtype=np.float64), int(maxiter)), p.stdin)
+            p.stdin.flush()
+            workers.append({"proc": p, "result": None})
         live = list(range(len(workers)))
-        while live:
-            asks, who = [], []
-            for i in list(live):
-                kind, payload = workers[i]["conn"].recv()
-                if kind == "done":
-                    workers[i]["result"] = payload
-                    live.remove(i)
-                else:
-                    asks.append(payload)
-                    who.append(i)
-            if asks:
-                laps = ev.lap_times(np.vstack(asks))  # one pipeline pass for this round's requests
-                for i, lap in zip(who, laps):
-                    workers[i]["conn"].send(float(lap))
-        out = []
-        for w in workers:
-            w["proc"].join()
-            out.append((float(ev.lap_times(w["result"])[0]), w["result"]))
-        return out
+        try:
+            while live:
+                asks, who = [], []
+                for i in list(live):
+                    kind, payload = pickle.load(workers[i]["proc"].stdout)
+                    if kind == "done":
+                        workers[i]["result"] = payload
+                        live.remove(i)
+                    else:
+                        asks.append(payload)
+                        who.append(i)
+                if asks:
+                    laps = ev.lap_times(np.vstack(asks))  # one pipeline pass for this round's requests
+                    for i, lap in zip(who, laps):
+                        pickle.dump(float(lap), workers[i]["proc"].stdin)
+                        workers[i]["proc"].stdin.flush()
+        finally:
+            for w in workers:
+                if w["result"] is None:
+                    w["proc"].kill()
+                w["proc"].stdin.close()
+                w["proc"].wait()
+        return [(float(ev.lap_times(w["result"])[0]), w["result"]) for w in workers]
 
     def Nonlinear(self, population=100, starts=10, key=None, maxiter=None):
         """Racing line by random search + local refinement (tbn.py:229-270): `population` random candidates
@@ -205,19 +212,3 @@ class TrajectoryBayesianNonlinear:
         self.best = self.updateAlphas(alpha_best)
         self.best_alphas, self.best_tau = np.asarray(alpha_best), float(tau_best)
         return time.time() - t0
-
-
-def _cobyla_worker(conn, tau0, alpha0, maxiter):
-    """Worker process of `optimize_COBYLA_lockstep`: scipy's COBYLA on the reference's objective
-    (tbn.py:207-227) with the lap time supplied by the parent.  No CUDA in here."""
-    from scipy.optimize import minimize
-
-    def objective(x):
-        conn.send(("ask", np.asarray(x, dtype=np.float64)))
-        tau = conn.recv()
-        return -max(0.0, tau0 - tau)
-
-    bounds = np.array([[ALPHA_LOW, ALPHA_HIGH] for _ in alpha0])
-    res = minimize(objective, x0=alpha0, bounds=bounds, method="COBYLA", options={"maxiter": maxiter, "disp": False})
-    conn.send(("done", np.asarray(res.x, dtype=np.float64)))
-    conn.close()
