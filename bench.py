@@ -5,15 +5,19 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" scores one population of `--candidates` (default 65,536 = BASELINE.json configs[1]) random
-alpha vectors per GPU: K1 spline+curvature -> K2 forward sweep -> K3 backward sweep + lap sum ->
-top-10 (-> one all-gather of 160 B/rank + merge when N > 1).  Candidates are independent, so ranks
-get disjoint populations and the scaling is weak.  Prints ONE JSON line (rank 0).
+alpha vectors per GPU: K1a spline solve -> K1b curvature (rotated write-out) -> K23 forward + backward
+sweeps with the lap sum -> top-10 (-> one all-gather of 160 B/rank + merge when N > 1).  Candidates are
+independent, so ranks get disjoint populations and the scaling is weak.  `--lanes` (default 3) steps are
+in flight at a time, each on its own stream (LapTimeEvaluator.lanes).  Prints ONE JSON line (rank 0).
 
-`value`   : whole-job evaluations/s, inputs already resident in HBM, CUDA-event timed, max over ranks.
-`e2e`     : same metric through the public host API (numpy in pinned memory -> H2D -> pipeline -> top-k
-            -> D2H of all lap times and the top-10) at N GPUs.
-`roofline`: the dominant kernel's algorithmic bytes / its CUDA-event duration against the measured HBM
-            peak (MEASURED_PEAKS.json, burst figure; fallback 6650 GB/s per B200_PROFILING.md).
+`value`   : whole-job evaluations/s, inputs already resident in HBM, CUDA events around exactly K steps,
+            max over ranks.
+`e2e`     : same metric through the public host API (LapTimeEvaluator.stream_populations): every step's
+            population goes pinned host memory -> H2D -> pipeline -> top-k -> D2H of all lap times and
+            the top-10 inside the timed region; copies and kernels of different steps overlap.
+`roofline`: the dominant kernel's algorithmic bytes / its CUDA-event duration (one population at a time,
+            ltk_eval_alphas_timed) against the measured HBM peak (MEASURED_PEAKS.json, burst figure;
+            fallback 6650 GB/s per B200_PROFILING.md); `pipeline` = the same for the whole step.
 `cpu_baseline` / `--impl reference`: the reference's own CPU path (oracle/reference_port.py: the
             reference restated one candidate at a time with the same SciPy/numpy calls, pinned
             bit-for-bit to the unmodified reference by tests/golden) on all host cores.
