@@ -1,7 +1,7 @@
 """BASELINE.json configs 3-5 on ONE B200 (the 8-GPU versions shard the same populations by rows):
 throughput with resident inputs, and parity of a random subsample against the C oracle (bit for bit).
 
-    python scripts/configs_probe.py [--quick]
+    python tests/configs_probe.py [--quick]
 """
 import os
 import sys
@@ -10,7 +10,7 @@ import time
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # tests/ -> repo root
 sys.path.insert(0, ROOT)
 import lap_time_optimization_b200 as ltk  # noqa: E402
 from oracle import c_oracle  # noqa: E402
