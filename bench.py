@@ -173,6 +173,19 @@ class ClockSampler:
                 "samples": len(picked)}
 
 
+def fp64_pipe_model(args, B, n, ms_per_step, clocks):
+    """FP64-pipe occupancy of one step under the instruction-cost model of profiles/README.md.
+    Cycles per sample and scheduler: K1b 75 (33 FP64 instructions), K23 forward 87 + backward 70 + lap term 23
+    (fp64 sweeps; the fp32 variant leaves only K1b and the fp64 lap sum on this pipe)."""
+    per_sample = 75 + (87 + 70 + 23 if args.sweep_bits == 64 else 4)
+    sms, schedulers = 148, 4
+    mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    need = B * n * per_sample / 32.0 / (sms * schedulers)
+    have = ms_per_step * 1e-3 * mhz * 1e6
+    return {"model_cycles_per_sample": per_sample, "frac": need / have, "sm_mhz": mhz,
+            "peak": "64 DFMA/clk/SM measured (tools/ubench/fp64_lat.cu): 37.2 TFLOP/s at 1965 MHz"}
+
+
 def hbm_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -315,6 +328,10 @@ def run_ours(args):
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_candidate": alg[dom],
                          "kernel_ms": {k: round(v, 4) for k, v in kt.items()},
+                         # the roof that actually binds (DESIGN.md section 3 "What binds"): FP64-pipe cycles per
+                         # sample from the SASS instruction counts and the measured issue costs (tools/ubench:
+                         # 2 cycles per FP64 warp instruction and scheduler, 3 for a three-register DFMA)
+                         "fp64_pipe": fp64_pipe_model(args, B, n, ms_total / args.steps, clocks),
                          "pipeline": {"bytes_per_candidate": a_staged,
                                       "achieved": a_staged * B * world / (ms_total / args.steps * 1e-3) / 1e9 / world,
                                       "frac": a_staged * B / (ms_total / args.steps * 1e-3) / 1e9 / peak}},
