@@ -435,3 +435,15 @@ def test_ns_change_reaches_every_lane(golden):
     for lo in (0, 65536, 2 * 65536, 3 * 65536):  # one slice per lane / chunk
         assert np.array_equal(second[lo:lo + 17], co2.lap_times(a[lo:lo + 17]))
     ev.close()
+
+
+@pytest.mark.parametrize("ns", [3, 4, 5, 6, 9, 33])
+def test_tiny_sampling_densities(ns):
+    """Degenerate lap lengths (2 .. 32 swept samples: no full register block, no middle row, a middle row only)
+    through all three sweep launch paths (one-chain kernel, two-chain kernel, split) for both vehicles."""
+    for name in ("buckmore_tbr18_bayes", "buckmore_mx5_bayes"):
+        ev, co = make(name, ns)
+        for B in (5, 20000, 70000):
+            a = np.random.default_rng(ns + B).uniform(0.0, 0.99, (B, ev.n_alpha))
+            assert np.array_equal(ev.lap_times(a), co.lap_times(a)), (name, ns, B)
+        ev.close()
