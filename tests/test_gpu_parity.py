@@ -447,3 +447,21 @@ def test_tiny_sampling_densities(ns):
             a = np.random.default_rng(ns + B).uniform(0.0, 0.99, (B, ev.n_alpha))
             assert np.array_equal(ev.lap_times(a), co.lap_times(a)), (name, ns, B)
         ev.close()
+
+
+def test_million_candidates_bit_exact_and_topk():
+    """BASELINE.json config 4 shape: 2^20 device-generated TBR18 candidates (chunked over the lanes), every lap time
+    against the C oracle bit for bit, top-10 against a stable host sort."""
+    ev, co = make("buckmore_tbr18_bayes")
+    B = 1 << 20
+    key = (4, 2026)
+    d_a = ev.random_population_device(B, key)
+    d_lap = ev.lap_times_device(d_a)
+    best, idx = ev.topk_device(d_lap, 10)
+    a = np.random.Generator(np.random.Philox(key=np.array(key, dtype=np.uint64))).uniform(0.0, 0.99, (B, ev.n_alpha))
+    want = co.lap_times(a)
+    got = d_lap.cpu().numpy()
+    assert np.array_equal(got, want)
+    order = np.lexsort((np.arange(B), want))[:10]
+    assert np.array_equal(idx.cpu().numpy(), order) and np.array_equal(best.cpu().numpy(), want[order])
+    ev.close()
