@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libltk.so")
+LIB_PATH = os.environ.get("LTK_LIB_PATH") or os.path.join(_HERE, "libltk.so")  # override: A/B builds of the library
 MAX_ENGINE_MAP = 16
 
 LTK_OK, LTK_E_ARG, LTK_E_CUDA, LTK_E_WORKSPACE, LTK_E_UNSUPPORTED = 0, -1, -2, -3, -4
