@@ -1,6 +1,6 @@
 """`VelocityProfile` facade -- the reference's three-pass profile (src/velocity.py:9-76) computed by
 the CUDA kernel `ltk_velocity_profile` for caller-supplied samples.  The batched pipeline
-(`LapTimeEvaluator`) fuses the same arithmetic into the K2/K3 sweep kernels."""
+(`LapTimeEvaluator`) fuses the same arithmetic into the K23 sweep kernel."""
 from __future__ import annotations
 
 import numpy as np
