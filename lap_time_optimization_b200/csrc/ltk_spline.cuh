@@ -231,8 +231,9 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a)
 
     // ---- K: curvature at the samples ----------------------------------------------------------------------
     const int g = tid % G, c = tid / G;
-    const int chunk = k1_chunk(n, CPT);
-    const int i0 = min(n, c * chunk), i1 = min(n, i0 + chunk);
+    // balanced chunks: every thread of a candidate gets n / CPT samples, the first n % CPT one more
+    const int cbase = n / CPT, cextra = n - cbase * CPT;
+    const int i0 = c * cbase + min(c, cextra), i1 = i0 + cbase + (c < cextra ? 1 : 0);
     const double step = LEN[g] / (double)(a.ns - 1);
     double best = -1.0;
     int bi = 0;
