@@ -105,31 +105,54 @@ __global__ void __launch_bounds__(K1A_THREADS, 4) k1a_solve(K1Args a)
         const double gamma = -b0d;
         const double p0 = (rhs < 2) ? S1(R, 0) : 0.0;
         const double dl = (rhs < 2) ? ddiv<false>(p0 - S1(R, N - 1), hl) : 0.0;  // closing chord slope
-        double pj = p0, dprev = dl, hprev = 0.0, cp = 0.0, r = 0.0;
-        for (int j = 0; j < N; ++j) {
-            const double hj = S1(H, j);
+        // rows 0 and N-1 are peeled: they carry the only special cases (no sub-diagonal in row 0, the
+        // Sherman-Morrison term and the closing slope in row N-1), so the N-2 rows between run branch-free
+        double pj = p0, dprev = dl, hprev, cp, r;
+        {   // row 0
+            const double hj = h0;
             double f;
             if (rhs < 2) {
-                double dj = dl;
-                if (j + 1 < N) {
-                    const double pn = S1(R, j + 1);
-                    dj = ddiv<false>(pn - pj, hj);
-                    pj = pn;
-                }
+                const double pn = S1(R, 1);
+                const double dj = ddiv<false>(pn - pj, hj);
+                pj = pn;
                 f = 6.0 * (dj - dprev);
                 dprev = dj;
             } else {
-                f = (j == 0) ? gamma : ((j == N - 1) ? hl : 0.0);
+                f = gamma;
+            }
+            const double inv = ddiv<false>(1.0, b0d - gamma);
+            cp = hj * inv;
+            r = f * inv;
+            S1(CP, 0) = cp;
+            S1(R, 0) = r;
+            hprev = hj;
+        }
+        for (int j = 1; j < N - 1; ++j) {
+            const double hj = S1(H, j);
+            double f = 0.0;
+            if (rhs < 2) {
+                const double pn = S1(R, j + 1);
+                const double dj = ddiv<false>(pn - pj, hj);
+                pj = pn;
+                f = 6.0 * (dj - dprev);
+                dprev = dj;
             }
             const double aa = hprev;
-            const double bbd = (j == 0) ? b0d - gamma : ((j == N - 1) ? 2.0 * (hprev + hl) - hl * hl / gamma : 2.0 * (aa + hj));
-            const double den = (j == 0) ? bbd : bbd - aa * cp;
-            const double inv = ddiv<false>(1.0, den);
+            const double inv = ddiv<false>(1.0, 2.0 * (aa + hj) - aa * cp);
             cp = hj * inv;
-            r = (j == 0) ? f * inv : (f - aa * r) * inv;
+            r = (f - aa * r) * inv;
             S1(CP, j) = cp;  // the three warps store identical values
             S1(R, j) = r;
             hprev = hj;
+        }
+        {   // row N-1
+            const double f = (rhs < 2) ? 6.0 * (dl - dprev) : hl;
+            const double aa = hprev;
+            const double inv = ddiv<false>(1.0, (2.0 * (hprev + hl) - hl * hl / gamma) - aa * cp);
+            cp = hl * inv;
+            r = (f - aa * r) * inv;
+            S1(CP, N - 1) = cp;
+            S1(R, N - 1) = r;
         }
         for (int j = N - 2; j >= 0; --j) {  // back substitution
             r = S1(R, j) - S1(CP, j) * r;
