@@ -300,11 +300,13 @@ def run_ours(args):
         peak, peak_src = hbm_peak()
         # algorithmic bytes per candidate of each kernel: the shares of A_staged;
         # the K1a -> K1b hand-off (second derivatives, knots) is not in the model and not counted
-        sweep_bytes = 32 * n + 8 if args.sweep_bits == 64 else 24 * n + 8  # fp32 sweeps park 4-byte velocities
-        alg = {"k1a_spline_solve": 8 * na, "k1b_curvature": 8 * n, "k23_sweep": sweep_bytes}
+        # fp32 sweeps read K1b's 4-byte copy of the curvature and park 4-byte velocities
+        sweep_bytes = 32 * n + 8 if args.sweep_bits == 64 else 16 * n + 8
+        k1b_bytes = 8 * n if args.sweep_bits == 64 else 12 * n
+        alg = {"k1a_spline_solve": 8 * na, "k1b_curvature": k1b_bytes, "k23_sweep": sweep_bytes}
         dom = max(kt, key=lambda k: kt[k])
         achieved = alg[dom] * B / (kt[dom] * 1e-3) / 1e9
-        a_staged = 8 * na + 8 * n + sweep_bytes  # 8 Na + 40 n + 8 for fp64
+        a_staged = 8 * na + k1b_bytes + sweep_bytes  # 8 Na + 40 n + 8 for fp64
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):

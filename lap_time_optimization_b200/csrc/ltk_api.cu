@@ -379,6 +379,9 @@ int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m
     a.left = ctx->d_left; a.diff = ctx->d_diff; a.N = ctx->N; a.ns = ctx->ns;
     a.B = B; a.Bp = w.Bp;
     a.kap = reinterpret_cast<double*>(ws + w.kap_off);
+    // fp32 sweeps read an fp32 copy of the curvature, kept in the upper half of the staging array (its lower
+    // half holds the fp32 parked velocities); only the current K1b writes it
+    a.kap32 = nullptr;
     a.rot = reinterpret_cast<int*>(ws + w.rot_off);
     a.len = reinterpret_cast<double*>(ws + w.len_off);
     a.mx = reinterpret_cast<double*>(ws + w.mx_off);
@@ -387,6 +390,8 @@ int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m
     if (ev) LTK_CUDA(ctx, cudaEventRecord(ev[0], st));
     if (k1_one_kernel) {
         a.staged = 1;
+        if (ctx->sweep_bits == 32 && !dumps && !k1_only)
+            a.kap32 = reinterpret_cast<float*>(ws + w.vacc_off) + (size_t)(ctx->ns - 1) * (size_t)w.Bp;
         LTK_CUDA(ctx, launch_k1a_solve(ctx, a, st));
         if (ev) LTK_CUDA(ctx, cudaEventRecord(ev[1], st));
         LTK_CUDA(ctx, launch_k1f_cfg(fcfg, a, st));
@@ -404,10 +409,17 @@ int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m
         f.kap = a.kap;
         f.stage = reinterpret_cast<float*>(ws + w.vacc_off);
         f.len = a.len; f.lap = d_lap; f.ns = ctx->ns; f.B = B; f.Bp = w.Bp;
+        f.kap32 = a.kap32;
         unsigned g32 = (unsigned)((B + F32_THREADS - 1) / F32_THREADS);
-        if (ctx->veh.kind == 0 && ctx->veh.n_map <= 8) k23_f32<0, 8><<<g32, F32_THREADS, 0, st>>>(f, ctx->veh32);
-        else if (ctx->veh.kind == 0) k23_f32<0, 16><<<g32, F32_THREADS, 0, st>>>(f, ctx->veh32);
-        else k23_f32<1, 8><<<g32, F32_THREADS, 0, st>>>(f, ctx->veh32);
+        if (f.kap32) {
+            if (ctx->veh.kind == 0 && ctx->veh.n_map <= 8) k23_f32<0, 8, true><<<g32, F32_THREADS, 0, st>>>(f, ctx->veh32);
+            else if (ctx->veh.kind == 0) k23_f32<0, 16, true><<<g32, F32_THREADS, 0, st>>>(f, ctx->veh32);
+            else k23_f32<1, 8, true><<<g32, F32_THREADS, 0, st>>>(f, ctx->veh32);
+        } else {
+            if (ctx->veh.kind == 0 && ctx->veh.n_map <= 8) k23_f32<0, 8, false><<<g32, F32_THREADS, 0, st>>>(f, ctx->veh32);
+            else if (ctx->veh.kind == 0) k23_f32<0, 16, false><<<g32, F32_THREADS, 0, st>>>(f, ctx->veh32);
+            else k23_f32<1, 8, false><<<g32, F32_THREADS, 0, st>>>(f, ctx->veh32);
+        }
         if (ev) { LTK_CUDA(ctx, cudaEventRecord(ev[3], st)); LTK_CUDA(ctx, cudaEventRecord(ev[4], st)); }
         g_launches.fetch_add(1);
         LTK_CUDA(ctx, cudaGetLastError());

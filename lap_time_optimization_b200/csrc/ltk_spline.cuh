@@ -317,10 +317,13 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a)
     {
         const int q0 = ROT[g];
         double* dst = a.kap + tile_base(b0 + g, n);
+        float* dst32 = a.kap32 ? a.kap32 + tile_base(b0 + g, n) : nullptr;
         for (int i = c; i < n; i += CPT) {
             int q = i + q0;
             q = (q >= n) ? q - n : q;
-            dst[(size_t)i * TILE] = KT[(size_t)q * G + g];
+            const double k = KT[(size_t)q * G + g];
+            dst[(size_t)i * TILE] = k;
+            if (dst32) dst32[(size_t)i * TILE] = (float)k;
         }
     }
 }

@@ -10,12 +10,14 @@
 //     `sqrt.approx`, `rsqrt.approx`, `rcp.approx`) -- with correctly rounded sqrtf and division the
 //     kernel was no faster than the fp64 one (0.94 ms against 0.53 ms, measured) and the 1e-4 budget is
 //     four orders of magnitude above these errors;
-//   * the curvature is still the fp64 one K1b wrote (read as fp64, rounded once); parked velocities are
-//     fp32, so the staging traffic halves: 16 n + 8 n bytes per candidate instead of 32 n;
+//   * the curvature is still computed in fp64 by K1b, which also writes it rounded to fp32 for this
+//     kernel; parked velocities are fp32: 8 n + 8 n bytes per candidate here instead of 32 n
+//     (+ 4 n for K1b's second copy);
 //   * np.diff(s) is taken as the constant step L / (ns - 1) (its fp64 values differ from it by 1e-13);
 //   * the lap-time sum is accumulated in fp64.
 // Measured error against the fp64 kernels: see tests/test_gpu_parity.py::test_fp32_sweep_variant.
 #pragma once
+#include <type_traits>
 
 namespace ltk {
 
@@ -23,7 +25,8 @@ constexpr int F32_THREADS = 128;
 constexpr int F32_UNROLL = 4;
 
 struct F32Args {
-    const double* kap;  // [n][tile-blocked] rotated curvature (fp64, from K1b)
+    const double* kap;   // [n][tile-blocked] rotated curvature (fp64, from K1b)
+    const float* kap32;  // the same rounded to fp32 by K1b (K32 kernels read this one: half the bytes)
     float* stage;       // [n][tile-blocked] parking array, fp32 (aliases the fp64 staging array)
     const double* len;
     double* lap;        // [B]
@@ -76,9 +79,12 @@ __device__ __forceinline__ float traction_f32(const VehF32& V, float v, float w,
     return (V.f_max <= fl) ? 0.0f : sqrt_fast(V.f_max_sq - fl * fl);           // vehicle.py:33-35
 }
 
-template <int KIND, int NPAD>
+// K32: the curvature comes from K1b's fp32 copy (same values as rounding the fp64 one here)
+template <int KIND, int NPAD, bool K32>
 __global__ void __launch_bounds__(F32_THREADS) k23_f32(F32Args a, VehF32 V)
 {
+    using KT_ = typename std::conditional<K32, float, double>::type;
+    const KT_* kap = K32 ? reinterpret_cast<const KT_*>(a.kap32) : reinterpret_cast<const KT_*>(a.kap);
     constexpr int U = F32_UNROLL;
     constexpr size_t P = TILE;
     __shared__ float sb[LTK_MAX_ENGINE_MAP + 1], sf[LTK_MAX_ENGINE_MAP + 1], ss[LTK_MAX_ENGINE_MAP + 1];
@@ -95,7 +101,7 @@ __global__ void __launch_bounds__(F32_THREADS) k23_f32(F32Args a, VehF32 V)
     const float root_mug = sqrtf(V.mu_g);        // v_local = sqrt(mu g / k) = sqrt(mu g) * rsqrt(k)
 
     // row 0 = the slowest sample: both chains start from v_local there (velocity.py:34-36, :58-61)
-    const float k0 = (float)a.kap[base];
+    const float k0 = (float)kap[base];
     const float v0 = root_mug * rsqrt_fast(k0);
     float vf = v0, kf = k0, vb = v0, kb = k0;
     double lap = (double)(ds * rcp_fast(v0));
@@ -121,8 +127,8 @@ __global__ void __launch_bounds__(F32_THREADS) k23_f32(F32Args a, VehF32 V)
 
     const int rows = n - 1, h = rows / 2;
     const bool has_mid = rows & 1;
-    const double* kfp = a.kap + base + P;
-    const double* kbp = a.kap + base + (size_t)(n - 1) * P;
+    const KT_* kfp = kap + base + P;
+    const KT_* kbp = kap + base + (size_t)(n - 1) * P;
     // the fp32 staging array uses the fp64 array's element index (its second half stays unused)
     float* sfp = a.stage + base + P;
     float* sbp = a.stage + base + (size_t)(n - 1) * P;
@@ -130,19 +136,19 @@ __global__ void __launch_bounds__(F32_THREADS) k23_f32(F32Args a, VehF32 V)
     // ---- phase 1: park (loads run one block of U rows ahead of their use) -------------------------------
     int t = 0;
     {
-        double fc[U], bc[U], fn[U], bn[U];
+        KT_ fc[U], bc[U], fn[U], bn[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const bool in = (u < h);
-            fc[u] = in ? kfp[(size_t)u * P] : 1.0;
-            bc[u] = in ? *(kbp - (size_t)u * P) : 1.0;
+            fc[u] = in ? kfp[(size_t)u * P] : (KT_)1;
+            bc[u] = in ? *(kbp - (size_t)u * P) : (KT_)1;
         }
         for (; t + U <= h; t += U) {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const bool in = (t + U + u < h);
-                fn[u] = in ? kfp[(size_t)(U + u) * P] : 1.0;
-                bn[u] = in ? *(kbp - (size_t)(U + u) * P) : 1.0;
+                fn[u] = in ? kfp[(size_t)(U + u) * P] : (KT_)1;
+                bn[u] = in ? *(kbp - (size_t)(U + u) * P) : (KT_)1;
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -168,13 +174,13 @@ __global__ void __launch_bounds__(F32_THREADS) k23_f32(F32Args a, VehF32 V)
     // ---- phase 2: meet the parked values, minimum, lap sum -------------------------------------------------
     t = 0;
     {
-        double fc[U], bc[U], fn[U], bn[U];
+        KT_ fc[U], bc[U], fn[U], bn[U];
         float fo[U], bo[U], fon[U], bon[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const bool in = (u < h);
-            fc[u] = in ? kfp[(size_t)u * P] : 1.0;
-            bc[u] = in ? *(kbp - (size_t)u * P) : 1.0;
+            fc[u] = in ? kfp[(size_t)u * P] : (KT_)1;
+            bc[u] = in ? *(kbp - (size_t)u * P) : (KT_)1;
             fo[u] = in ? sfp[(size_t)u * P] : 1.0f;
             bo[u] = in ? *(sbp - (size_t)u * P) : 1.0f;
         }
@@ -182,8 +188,8 @@ __global__ void __launch_bounds__(F32_THREADS) k23_f32(F32Args a, VehF32 V)
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const bool in = (t + U + u < h);
-                fn[u] = in ? kfp[(size_t)(U + u) * P] : 1.0;
-                bn[u] = in ? *(kbp - (size_t)(U + u) * P) : 1.0;
+                fn[u] = in ? kfp[(size_t)(U + u) * P] : (KT_)1;
+                bn[u] = in ? *(kbp - (size_t)(U + u) * P) : (KT_)1;
                 fon[u] = in ? sfp[(size_t)(U + u) * P] : 1.0f;
                 bon[u] = in ? *(sbp - (size_t)(U + u) * P) : 1.0f;
             }

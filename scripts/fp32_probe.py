@@ -24,7 +24,7 @@ for veh in ("tbr18", "MX5"):
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / 96
             kt = ev.kernel_times(pops[0], outs[0], reps=5)
-            bytes_per = 8 * 43 + (40 if bits == 64 else 32) * 846 + 8
+            bytes_per = 8 * 43 + (40 if bits == 64 else 28) * 846 + 8
             print(f"{veh} fp{bits} lanes {lanes}: {ms:.4f} ms/step {B / ms / 1e3:.1f} M evals/s, {B * bytes_per / ms / 1e6:.0f} GB/s algorithmic; kernels {kt}")
     rel = np.abs(res[32] - res[64]) / res[64]
     print(f"{veh}: fp32 sweeps vs fp64: median {np.median(rel):.2e} p99 {np.percentile(rel, 99):.2e} max {rel.max():.2e}")
