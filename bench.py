@@ -207,6 +207,10 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    cpu_result = None
+    if world == 1 and not args.no_cpu_baseline:
+        # the CPU baseline forks a worker pool: do it before this process owns a CUDA context
+        cpu_result = cpu_rate(args, args.cpu_sample, os.cpu_count() or 1)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -338,9 +342,9 @@ def run_ours(args):
                                       "achieved": a_staged * B * world / (ms_total / args.steps * 1e-3) / 1e9 / world,
                                       "frac": a_staged * B / (ms_total / args.steps * 1e-3) / 1e9 / peak}},
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if cpu_result is not None:
             cores = os.cpu_count() or 1
-            rate, cpu_laps, cpu_a = cpu_rate(args, args.cpu_sample, cores)
+            rate, cpu_laps, cpu_a = cpu_result
             gpu_laps = ev.lap_times(cpu_a)
             rel = np.abs(gpu_laps - cpu_laps) / cpu_laps
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
