@@ -75,6 +75,19 @@ int ltk_set_ns(ltk_ctx *ctx, int ns);
  * Affects ltk_eval_alphas / ltk_eval_controls; ltk_profile always uses fp64. */
 int ltk_set_sweep_precision(ltk_ctx *ctx, int bits);
 
+/* Tracing: after ltk_trace_begin(ctx, n) every kernel launch of ltk_eval_* on this context records a CUDA
+ * event before and after itself on its stream (up to n launches; n = 0 switches tracing off).
+ * ltk_trace_read waits for the recorded launches and returns kind (LTK_TRACE_*), start and end in
+ * milliseconds relative to the FIRST record of `base` (another traced context of the same device, or
+ * NULL for ctx itself), so that contexts working side by side can be put on one time line.  The
+ * reference only brackets whole optimiser runs with time.time() (trajectory.py:67-170). */
+#define LTK_TRACE_K1A 1
+#define LTK_TRACE_K1B 2
+#define LTK_TRACE_K23 3
+int ltk_trace_begin(ltk_ctx *ctx, int max_records);
+int ltk_trace_read(ltk_ctx *ctx, const ltk_ctx *base, int max_records, int *h_kind, float *h_start_ms,
+                   float *h_end_ms, int *n_out);
+
 /* Scheduling knob, no effect on results.  on (default): a population that fills the sweep kernel's warp
  * slots unevenly (65,536 candidates = 3.46 warps per scheduler) is split -- whole layers of one warp per
  * scheduler to the two-chain kernel, the remainder to the one-chain kernel on a second stream of the

@@ -31,6 +31,10 @@ struct ltk_ctx {
     cudaStream_t aux_stream;  // the remainder sweep (see run_pipeline) runs next to the main one
     cudaEvent_t aux_ev[2];
     int sweep_remainder;      // 0 disables the split (LTK_SWEEP_REMAINDER=0)
+    // tracing (ltk_trace_*): one (start, end) event pair per kernel launch of the pipeline
+    cudaEvent_t* trace_ev;    // [2 * trace_cap]
+    int* trace_kind;          // LTK_TRACE_K1A ...
+    int trace_cap, trace_n;
     void* d_profile_ws;
     size_t profile_ws_bytes;
     int k1_g_override, k1_staged_override, k1_threads_override, sweep_mode, k1_mode;
@@ -387,14 +391,30 @@ int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m
     a.mx = reinterpret_cast<double*>(ws + w.mx_off);
     a.my = reinterpret_cast<double*>(ws + w.my_off);
     a.knots = reinterpret_cast<double*>(ws + w.knots_off);
+    auto trace_open = [&](int kind, cudaStream_t s_) {
+        if (ctx->trace_ev && ctx->trace_n < ctx->trace_cap) {
+            ctx->trace_kind[ctx->trace_n] = kind;
+            cudaEventRecord(ctx->trace_ev[2 * ctx->trace_n], s_);
+        }
+    };
+    auto trace_close = [&](cudaStream_t s_) {
+        if (ctx->trace_ev && ctx->trace_n < ctx->trace_cap) {
+            cudaEventRecord(ctx->trace_ev[2 * ctx->trace_n + 1], s_);
+            ++ctx->trace_n;
+        }
+    };
     if (ev) LTK_CUDA(ctx, cudaEventRecord(ev[0], st));
     if (k1_one_kernel) {
         a.staged = 1;
         if (ctx->sweep_bits == 32 && !dumps && !k1_only)
             a.kap32 = reinterpret_cast<float*>(ws + w.vacc_off) + (size_t)(ctx->ns - 1) * (size_t)w.Bp;
+        trace_open(LTK_TRACE_K1A, st);
         LTK_CUDA(ctx, launch_k1a_solve(ctx, a, st));
+        trace_close(st);
         if (ev) LTK_CUDA(ctx, cudaEventRecord(ev[1], st));
+        trace_open(LTK_TRACE_K1B, st);
         LTK_CUDA(ctx, launch_k1f_cfg(fcfg, a, st));
+        trace_close(st);
     } else {
         a.staged = cfg.staged;
         LTK_CUDA(ctx, launch_k1a(ctx, a, st));
@@ -411,6 +431,7 @@ int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m
         f.len = a.len; f.lap = d_lap; f.ns = ctx->ns; f.B = B; f.Bp = w.Bp;
         f.kap32 = a.kap32;
         unsigned g32 = (unsigned)((B + F32_THREADS - 1) / F32_THREADS);
+        trace_open(LTK_TRACE_K23, st);
         if (f.kap32) {
             if (ctx->veh.kind == 0 && ctx->veh.n_map <= 8) k23_f32<0, 8, true><<<g32, F32_THREADS, 0, st>>>(f, ctx->veh32);
             else if (ctx->veh.kind == 0) k23_f32<0, 16, true><<<g32, F32_THREADS, 0, st>>>(f, ctx->veh32);
@@ -420,6 +441,7 @@ int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m
             else if (ctx->veh.kind == 0) k23_f32<0, 16, false><<<g32, F32_THREADS, 0, st>>>(f, ctx->veh32);
             else k23_f32<1, 8, false><<<g32, F32_THREADS, 0, st>>>(f, ctx->veh32);
         }
+        trace_close(st);
         if (ev) { LTK_CUDA(ctx, cudaEventRecord(ev[3], st)); LTK_CUDA(ctx, cudaEventRecord(ev[4], st)); }
         g_launches.fetch_add(1);
         LTK_CUDA(ctx, cudaGetLastError());
@@ -467,6 +489,7 @@ int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m
             f.first = 0; f.last = whole;
             gridf = (unsigned)(whole / FUSED_THREADS);
         }
+        trace_open(LTK_TRACE_K23, st);
         if (roles) {
             if (ctx->veh.kind == 0) {
                 if (ctx->veh.lut_top >= 0) k23_roles<0, 0><<<gridr, ROLES_THREADS, 0, st>>>(f, ctx->veh);
@@ -483,6 +506,7 @@ int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m
             k23_sweep<1, 8><<<gridf, FUSED_THREADS, 0, st>>>(f, ctx->veh);
         }
         if (split) LTK_CUDA(ctx, cudaStreamWaitEvent(st, ctx->aux_ev[1], 0));
+        trace_close(st);
         if (ev) { LTK_CUDA(ctx, cudaEventRecord(ev[3], st)); LTK_CUDA(ctx, cudaEventRecord(ev[4], st)); }
         g_launches.fetch_add(1);
     }
@@ -631,6 +655,10 @@ void ltk_destroy(ltk_ctx* ctx)
     cudaFree(ctx->d_lut);
     for (int i = 0; i < 2; ++i) { cudaFree(ctx->d_topk_lap[i]); cudaFree(ctx->d_topk_idx[i]); }
     cudaFree(ctx->d_ticket);
+    if (ctx->trace_ev) {
+        for (int i = 0; i < 2 * ctx->trace_cap; ++i) cudaEventDestroy(ctx->trace_ev[i]);
+        free(ctx->trace_ev); free(ctx->trace_kind);
+    }
     if (ctx->aux_stream) { cudaStreamDestroy(ctx->aux_stream); cudaEventDestroy(ctx->aux_ev[0]); cudaEventDestroy(ctx->aux_ev[1]); }
     cudaFree(ctx->d_profile_ws);
     delete ctx;
@@ -656,6 +684,43 @@ int ltk_set_sweep_precision(ltk_ctx* ctx, int bits)
     if (!ctx) return LTK_E_ARG;
     if (bits != 64 && bits != 32) return fail(ctx, LTK_E_ARG, "sweep precision must be 64 or 32");
     ctx->sweep_bits = bits;
+    return LTK_OK;
+}
+
+int ltk_trace_begin(ltk_ctx* ctx, int max_records)
+{
+    if (!ctx || max_records < 0) return LTK_E_ARG;
+    DeviceGuard guard(ctx->device);
+    if (ctx->trace_ev) {
+        for (int i = 0; i < 2 * ctx->trace_cap; ++i) cudaEventDestroy(ctx->trace_ev[i]);
+        free(ctx->trace_ev); free(ctx->trace_kind);
+        ctx->trace_ev = nullptr; ctx->trace_kind = nullptr; ctx->trace_cap = ctx->trace_n = 0;
+    }
+    if (max_records == 0) return LTK_OK;
+    ctx->trace_ev = static_cast<cudaEvent_t*>(calloc(2 * (size_t)max_records, sizeof(cudaEvent_t)));
+    ctx->trace_kind = static_cast<int*>(calloc((size_t)max_records, sizeof(int)));
+    if (!ctx->trace_ev || !ctx->trace_kind) return fail(ctx, LTK_E_ARG, "out of host memory");
+    for (int i = 0; i < 2 * max_records; ++i) LTK_CUDA(ctx, cudaEventCreate(&ctx->trace_ev[i]));
+    ctx->trace_cap = max_records;
+    ctx->trace_n = 0;
+    return LTK_OK;
+}
+
+int ltk_trace_read(ltk_ctx* ctx, const ltk_ctx* base, int max_records, int* h_kind, float* h_start_ms, float* h_end_ms,
+                   int* n_out)
+{
+    if (!ctx || !n_out || (max_records > 0 && (!h_kind || !h_start_ms || !h_end_ms))) return LTK_E_ARG;
+    const ltk_ctx* b = base ? base : ctx;
+    if (!ctx->trace_ev || !b->trace_ev || b->trace_n < 1) { *n_out = 0; return LTK_OK; }
+    DeviceGuard guard(ctx->device);
+    int n = ctx->trace_n < max_records ? ctx->trace_n : max_records;
+    for (int i = 0; i < n; ++i) {
+        LTK_CUDA(ctx, cudaEventSynchronize(ctx->trace_ev[2 * i + 1]));
+        h_kind[i] = ctx->trace_kind[i];
+        LTK_CUDA(ctx, cudaEventElapsedTime(&h_start_ms[i], b->trace_ev[0], ctx->trace_ev[2 * i]));
+        LTK_CUDA(ctx, cudaEventElapsedTime(&h_end_ms[i], b->trace_ev[0], ctx->trace_ev[2 * i + 1]));
+    }
+    *n_out = n;
     return LTK_OK;
 }
 

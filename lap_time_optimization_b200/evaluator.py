@@ -70,6 +70,27 @@ class LapTimeEvaluator:
         for lane in (getattr(self, "_lanes", None) or [])[1:]:
             lane.ev.set_ns(ns)
 
+    # -- tracing ------------------------------------------------------------------------------------
+    def trace_begin(self, max_records=256):
+        """Record a CUDA event before and after every pipeline kernel of this evaluator and of its lanes."""
+        for ev in [self] + [lane.ev for lane in (getattr(self, "_lanes", None) or [])[1:]]:
+            _native.check(self.lib.ltk_trace_begin(ev._ctx, int(max_records)), ev._ctx)
+
+    def trace_read(self):
+        """[(lane, kernel, start_ms, end_ms)] of everything recorded since `trace_begin`, on one time line
+        (zero = the first kernel this evaluator launched), sorted by start; switches tracing off."""
+        names = {1: "k1a", 2: "k1b", 3: "k23"}
+        evs = [self] + [lane.ev for lane in (getattr(self, "_lanes", None) or [])[1:]]
+        out = []
+        for li, ev in enumerate(evs):
+            cap = 4096
+            kind, t0, t1, n = (C.c_int * cap)(), (C.c_float * cap)(), (C.c_float * cap)(), C.c_int()
+            _native.check(self.lib.ltk_trace_read(ev._ctx, self._ctx, cap, kind, t0, t1, C.byref(n)), ev._ctx)
+            out += [(li, names.get(kind[i], "?"), float(t0[i]), float(t1[i])) for i in range(n.value)]
+        for ev in evs:
+            _native.check(self.lib.ltk_trace_begin(ev._ctx, 0), ev._ctx)
+        return sorted(out, key=lambda r: r[2])
+
     def set_sweep_precision(self, bits):
         """64 (default): everything in fp64.  32: the optional fp32 variant of the velocity sweeps (spline and
         curvature stay fp64; lap times then agree with the fp64 ones to ~1e-5, tolerance 1e-4)."""
