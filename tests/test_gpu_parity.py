@@ -465,3 +465,17 @@ def test_million_candidates_bit_exact_and_topk():
     order = np.lexsort((np.arange(B), want))[:10]
     assert np.array_equal(idx.cpu().numpy(), order) and np.array_equal(best.cpu().numpy(), want[order])
     ev.close()
+
+
+def test_kernel_trace(buckmore):
+    """ltk_trace_*: one (start, end) record per pipeline kernel, in launch order, on one time line."""
+    ev, _ = buckmore
+    a = ev.random_population_device(40000, (1, 2))
+    ev.trace_begin(16)
+    ev.lap_times_device(a)
+    ev.lap_times_device(a)
+    rows = ev.trace_read()
+    assert [r[1] for r in rows] == ["k1a", "k1b", "k23"] * 2
+    assert rows[0][2] == 0.0 and all(r[3] >= r[2] for r in rows)
+    assert all(rows[i + 1][2] >= rows[i][3] - 1e-3 for i in range(len(rows) - 1))  # one stream: back to back
+    assert ev.trace_read() == []  # reading switches tracing off
