@@ -4,11 +4,20 @@ from __future__ import annotations
 
 import json
 import re
-from math import sqrt
 
 from ._native import LtkVehicle
+from .vehicle import GRAV, announce, friction_circle
 
-GRAV = 9.81  # m/s^2 (vehicleMX5.py:6)
+# attribute -> where it sits in the (commented) JSON document; the names are the ones callers of the
+# reference read (vehicleMX5.py:46-79)
+JSON_FIELDS = {
+    "rotational_inertia": ("rotational_inertia",), "name": ("name",), "mass": ("mass",),
+    "length_f": ("length_f",), "length_r": ("length_r",),
+    "B_f": ("frontTire", "B_f"), "C_f": ("frontTire", "C_f"), "D_f": ("frontTire", "D_f"),
+    "B_r": ("rearTire", "B_r"), "C_r": ("rearTire", "C_r"), "D_r": ("rearTire", "D_r"),
+    "C_m": ("control", "C_m"), "Cr_0": ("Cr_0",), "Cr_2": ("Cr_2",), "ptv": ("ptv",),
+    "T": ("control", "T"), "friction_coef": ("control", "lambda"), "ro_long": ("control", "ro_long"),
+}
 
 
 def _strip_json_comments(text):
@@ -19,56 +28,44 @@ def _strip_json_comments(text):
 class VehicleMX5:
     def __init__(self, vehicle_filepath, quiet=False):
         self.load_params(vehicle_filepath)
-        if not quiet:
-            print("[ Imported {} ]".format(self.name))
-
-    def engine_force(self, velocity, gear=None):
-        """Maximum longitudinal drive force (vehicleMX5.py:19-21)."""
-        return (self.T * self.C_m) - self.Cr_0 - (self.Cr_2 * (velocity**2))
-
-    def traction(self, v, k, lam=2.0):
-        """Force left inside the friction circle of radius lam*D*m*g (vehicleMX5.py:23-37)."""
-        D = (self.D_f + self.D_r) * 0.5
-        Fn = self.mass * GRAV
-        F_max = lam * D * Fn
-        F_lat = self.mass * v * v * k
-        if F_max <= F_lat:
-            return 0
-        return sqrt(F_max**2 - F_lat**2)
+        announce(self.name, quiet)
 
     def remove_comments(self, json_str):
         return _strip_json_comments(json_str)
 
     def load_params(self, vehicle_filepath):
-        """Field names follow vehicleMX5.py:46-79."""
-        with open(vehicle_filepath) as f:
-            data = json.loads(_strip_json_comments(f.read()))
-        self.rotational_inertia = data["rotational_inertia"]
-        self.name = data["name"]
-        self.mass = data["mass"]
-        self.length_f = data["length_f"]
-        self.length_r = data["length_r"]
-        self.B_f, self.C_f, self.D_f = (data["frontTire"][k] for k in ("B_f", "C_f", "D_f"))
-        self.B_r, self.C_r, self.D_r = (data["rearTire"][k] for k in ("B_r", "C_r", "D_r"))
-        self.C_m = data["control"]["C_m"]
-        self.Cr_0 = data["Cr_0"]
-        self.Cr_2 = data["Cr_2"]
-        self.ptv = data["ptv"]
-        self.T = data["control"]["T"]
-        self.friction_coef = data["control"]["lambda"]
-        self.ro_long = data["control"]["ro_long"]
+        with open(vehicle_filepath) as handle:
+            doc = json.loads(_strip_json_comments(handle.read()))
+        for attr, keys in JSON_FIELDS.items():
+            node = doc
+            for key in keys:
+                node = node[key]
+            setattr(self, attr, node)
+
+    def drive_offset(self):
+        """(T * C_m) - Cr_0: the speed-independent part of the drive force (vehicleMX5.py:21)."""
+        return (self.T * self.C_m) - self.Cr_0
+
+    def grip_limit(self, lam=2.0):
+        """lam * D * (m * g) with D the mean Pacejka peak factor of the two axles (vehicleMX5.py:28-33)."""
+        peak = (self.D_f + self.D_r) * 0.5
+        return lam * peak * (self.mass * GRAV)
+
+    def engine_force(self, velocity, gear=None):
+        """Maximum longitudinal drive force (vehicleMX5.py:19-21)."""
+        return self.drive_offset() - (self.Cr_2 * (velocity**2))
+
+    def traction(self, v, k, lam=2.0):
+        """Force left inside the friction circle of radius lam*D*m*g (vehicleMX5.py:23-37)."""
+        return friction_circle(self.grip_limit(lam), self.mass * v * v * k)
 
     def to_ltk(self, lam=2.0) -> LtkVehicle:
-        v = LtkVehicle()
-        v.kind = 1
-        v.n_map = 0
-        v.mass = float(self.mass)
-        v.mu_g = self.friction_coef * GRAV  # velocity.py:29 with friction_coef = control.lambda
-        D = (self.D_f + self.D_r) * 0.5
-        Fn = self.mass * GRAV
-        f = lam * D * Fn
-        v.f_max = f
-        v.f_max_sq = f**2
-        v.e0 = (self.T * self.C_m) - self.Cr_0
-        v.cr2 = self.Cr_2
-        return v
+        out = LtkVehicle()
+        out.kind, out.n_map = 1, 0
+        out.mass = float(self.mass)
+        out.mu_g = self.friction_coef * GRAV  # velocity.py:29 with friction_coef = control.lambda
+        out.f_max = self.grip_limit(lam)
+        out.f_max_sq = out.f_max**2
+        out.e0 = self.drive_offset()
+        out.cr2 = self.Cr_2
+        return out
