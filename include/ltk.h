@@ -109,6 +109,16 @@ int ltk_workspace_bytes(const ltk_ctx *ctx, int64_t B, size_t *out_bytes);
 int ltk_eval_alphas(ltk_ctx *ctx, const double *d_alphas, int64_t B, double *d_lap,
                     void *d_workspace, size_t workspace_bytes, void *stream);
 
+/* Host in, host out: h_alphas [B][n_ctrl] and h_lap [B] are ordinary host arrays; returns when h_lap is
+ * filled.  This is the call the reference's optimiser loops make once per objective evaluation --
+ * scipy's COBYLA through calcMinTime (trajectory_bayesian_nonlinear.py:207-227) and L-BFGS-B through
+ * Trajectory.lap_time (trajectory.py:128-146) -- batched over the finite-difference points or the
+ * lock-step starts.  The context owns the pinned staging, device buffers and stream; for B <= 16,384 the
+ * upload, K1a, K1b, K23 and the download are one instantiated CUDA graph per batch size (up to 8 sizes
+ * cached, rebuilt after ltk_set_*), so a call costs one graph launch and one stream synchronisation.
+ * Not for concurrent use on one context. */
+int ltk_eval_alphas_host(ltk_ctx *ctx, const double *h_alphas, int64_t B, double *h_lap);
+
 /* Measurement hook: same work as ltk_eval_alphas, with CUDA events recorded on `stream` around each
  * kernel; synchronises and writes the durations in milliseconds to h_ms[4] = {K1a, K1b, K23, -1}. */
 int ltk_eval_alphas_timed(ltk_ctx *ctx, const double *d_alphas, int64_t B, double *d_lap,

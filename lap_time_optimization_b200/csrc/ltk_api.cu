@@ -9,6 +9,9 @@
 
 using namespace ltk;
 
+#define LTK_HOST_GRAPHS 8          // cached graphs per context (least recently used one is replaced)
+#define LTK_HOST_GRAPH_MAX_B 16384  // larger host batches are launched directly (launch cost no longer matters)
+
 static std::atomic<long long> g_launches{0};
 static char g_create_err[256] = "";
 
@@ -37,6 +40,17 @@ struct ltk_ctx {
     int trace_cap, trace_n;
     void* d_profile_ws;
     size_t profile_ws_bytes;
+    // host-in / host-out small-batch path (ltk_eval_alphas_host): pinned staging, device buffers, a stream
+    // of its own and one instantiated CUDA graph (upload, K1a, K1b, K23, download) per batch size
+    cudaStream_t host_stream;
+    double *h_in, *h_out, *d_hin, *d_hout;
+    char* d_hws;
+    long long host_cap;      // candidates the buffers hold
+    size_t host_ws_bytes;
+    struct HostGraph { long long B; unsigned long long epoch; cudaGraphExec_t exec; } host_graph[LTK_HOST_GRAPHS];
+    unsigned long long epoch;  // bumped by every setter that changes what the pipeline launches
+    unsigned long long host_tick;
+    unsigned long long host_used[LTK_HOST_GRAPHS];
     int k1_g_override, k1_staged_override, k1_threads_override, sweep_mode, k1_mode;
     char err[256];
 };
@@ -661,6 +675,11 @@ void ltk_destroy(ltk_ctx* ctx)
     }
     if (ctx->aux_stream) { cudaStreamDestroy(ctx->aux_stream); cudaEventDestroy(ctx->aux_ev[0]); cudaEventDestroy(ctx->aux_ev[1]); }
     cudaFree(ctx->d_profile_ws);
+    for (int i = 0; i < LTK_HOST_GRAPHS; ++i)
+        if (ctx->host_graph[i].exec) cudaGraphExecDestroy(ctx->host_graph[i].exec);
+    if (ctx->host_stream) cudaStreamDestroy(ctx->host_stream);
+    cudaFreeHost(ctx->h_in); cudaFreeHost(ctx->h_out);
+    cudaFree(ctx->d_hin); cudaFree(ctx->d_hout); cudaFree(ctx->d_hws);
     delete ctx;
 }
 
@@ -676,6 +695,7 @@ int ltk_set_ns(ltk_ctx* ctx, int ns)
         ctx->ns = old;
         return fail(ctx, LTK_E_UNSUPPORTED, "no K1 configuration fits shared memory");
     }
+    ++ctx->epoch;
     return LTK_OK;
 }
 
@@ -684,6 +704,7 @@ int ltk_set_sweep_precision(ltk_ctx* ctx, int bits)
     if (!ctx) return LTK_E_ARG;
     if (bits != 64 && bits != 32) return fail(ctx, LTK_E_ARG, "sweep precision must be 64 or 32");
     ctx->sweep_bits = bits;
+    ++ctx->epoch;
     return LTK_OK;
 }
 
@@ -728,6 +749,7 @@ int ltk_set_sweep_split(ltk_ctx* ctx, int on)
 {
     if (!ctx) return LTK_E_ARG;
     ctx->sweep_remainder = on ? 1 : 0;
+    ++ctx->epoch;
     return LTK_OK;
 }
 
@@ -749,6 +771,97 @@ int ltk_eval_alphas(ltk_ctx* ctx, const double* d_alphas, int64_t B, double* d_l
     DeviceGuard guard(ctx->device);
     return run_pipeline(ctx, d_alphas, nullptr, 0, B, d_lap, static_cast<char*>(d_workspace), w, false,
                         static_cast<cudaStream_t>(stream));
+}
+
+// Host in, host out, one call: the latency path of the optimiser loops (finite-difference rounds of
+// N + 1 candidates, lock-step COBYLA rounds of one candidate per start).  The
+// upload, the three kernels and the download of one batch size are ONE instantiated CUDA graph, launched
+// on the context's own stream; the caller's arrays are ordinary (pageable) host memory.
+static int host_reserve(ltk_ctx* ctx, long long B)
+{
+    if (!ctx->host_stream) LTK_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->host_stream, cudaStreamNonBlocking));
+    const WsLayout w = ws_layout(ctx->ns, ctx->N, B, false);
+    if (B <= ctx->host_cap && w.total <= ctx->host_ws_bytes) return LTK_OK;
+    LTK_CUDA(ctx, cudaStreamSynchronize(ctx->host_stream));
+    for (int i = 0; i < LTK_HOST_GRAPHS; ++i)  // the graphs hold the old addresses
+        if (ctx->host_graph[i].exec) { cudaGraphExecDestroy(ctx->host_graph[i].exec); ctx->host_graph[i].exec = nullptr; }
+    if (B > ctx->host_cap) {
+        long long cap = ctx->host_cap ? ctx->host_cap : 64;
+        while (cap < B) cap *= 2;
+        cudaFreeHost(ctx->h_in); cudaFreeHost(ctx->h_out); cudaFree(ctx->d_hin); cudaFree(ctx->d_hout);
+        ctx->h_in = ctx->h_out = ctx->d_hin = ctx->d_hout = nullptr;
+        ctx->host_cap = 0;
+        const size_t in_bytes = sizeof(double) * (size_t)cap * (size_t)ctx->N;
+        LTK_CUDA(ctx, cudaMallocHost(&ctx->h_in, in_bytes));
+        LTK_CUDA(ctx, cudaMallocHost(&ctx->h_out, sizeof(double) * (size_t)cap));
+        LTK_CUDA(ctx, cudaMalloc(&ctx->d_hin, in_bytes));
+        LTK_CUDA(ctx, cudaMalloc(&ctx->d_hout, sizeof(double) * (size_t)cap));
+        ctx->host_cap = cap;
+    }
+    const size_t need = ws_layout(ctx->ns, ctx->N, ctx->host_cap, false).total;
+    if (need > ctx->host_ws_bytes) {
+        cudaFree(ctx->d_hws);
+        ctx->d_hws = nullptr; ctx->host_ws_bytes = 0;
+        LTK_CUDA(ctx, cudaMalloc(&ctx->d_hws, need));
+        ctx->host_ws_bytes = need;
+    }
+    return LTK_OK;
+}
+
+static int host_enqueue(ltk_ctx* ctx, long long B)
+{
+    const WsLayout w = ws_layout(ctx->ns, ctx->N, B, false);
+    cudaStream_t st = ctx->host_stream;
+    LTK_CUDA(ctx, cudaMemcpyAsync(ctx->d_hin, ctx->h_in, sizeof(double) * (size_t)B * (size_t)ctx->N, cudaMemcpyHostToDevice, st));
+    int rc = run_pipeline(ctx, ctx->d_hin, nullptr, 0, B, ctx->d_hout, ctx->d_hws, w, false, st);
+    if (rc != LTK_OK) return rc;
+    LTK_CUDA(ctx, cudaMemcpyAsync(ctx->h_out, ctx->d_hout, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, st));
+    return LTK_OK;
+}
+
+int ltk_eval_alphas_host(ltk_ctx* ctx, const double* h_alphas, int64_t B, double* h_lap)
+{
+    if (!ctx) return LTK_E_ARG;
+    if (B == 0) return LTK_OK;
+    if (!h_alphas || !h_lap || B < 0) return fail(ctx, LTK_E_ARG, "null or negative argument");
+    DeviceGuard guard(ctx->device);
+    int rc = host_reserve(ctx, B);
+    if (rc != LTK_OK) return rc;
+    memcpy(ctx->h_in, h_alphas, sizeof(double) * (size_t)B * (size_t)ctx->N);
+    const bool use_graph = B <= LTK_HOST_GRAPH_MAX_B && !ctx->trace_ev && !getenv("LTK_NO_GRAPH");
+    if (use_graph) {
+        int slot = -1, victim = 0;
+        for (int i = 0; i < LTK_HOST_GRAPHS; ++i) {
+            if (ctx->host_graph[i].exec && ctx->host_graph[i].B == B && ctx->host_graph[i].epoch == ctx->epoch) { slot = i; break; }
+            if (ctx->host_used[i] < ctx->host_used[victim]) victim = i;
+        }
+        if (slot < 0) {
+            slot = victim;
+            if (ctx->host_graph[slot].exec) { cudaGraphExecDestroy(ctx->host_graph[slot].exec); ctx->host_graph[slot].exec = nullptr; }
+            cudaGraph_t graph = nullptr;
+            LTK_CUDA(ctx, cudaStreamBeginCapture(ctx->host_stream, cudaStreamCaptureModeThreadLocal));
+            const long long before = g_launches.load();
+            rc = host_enqueue(ctx, B);
+            cudaError_t e = cudaStreamEndCapture(ctx->host_stream, &graph);
+            g_launches.store(before);  // captured, not launched
+            if (rc != LTK_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (e != cudaSuccess) return fail(ctx, LTK_E_CUDA, "cudaStreamEndCapture", e);
+            e = cudaGraphInstantiate(&ctx->host_graph[slot].exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e != cudaSuccess) { ctx->host_graph[slot].exec = nullptr; return fail(ctx, LTK_E_CUDA, "cudaGraphInstantiate", e); }
+            ctx->host_graph[slot].B = B;
+            ctx->host_graph[slot].epoch = ctx->epoch;
+        }
+        ctx->host_used[slot] = ++ctx->host_tick;
+        LTK_CUDA(ctx, cudaGraphLaunch(ctx->host_graph[slot].exec, ctx->host_stream));
+        g_launches.fetch_add(3);  // K1a, K1b, K23 inside the graph
+    } else {
+        rc = host_enqueue(ctx, B);
+        if (rc != LTK_OK) return rc;
+    }
+    LTK_CUDA(ctx, cudaStreamSynchronize(ctx->host_stream));
+    memcpy(h_lap, ctx->h_out, sizeof(double) * (size_t)B);
+    return LTK_OK;
 }
 
 int ltk_eval_alphas_timed(ltk_ctx* ctx, const double* d_alphas, int64_t B, double* d_lap, void* d_workspace,

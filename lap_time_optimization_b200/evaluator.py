@@ -172,6 +172,10 @@ class LapTimeEvaluator:
     # over the lanes: measured (B200, 2^20 Buckmore/TBR18 candidates) 17.2 ms as one multi-wave launch
     # sequence with a 15 GB workspace, against ~13 ms in 65,536-candidate chunks three at a time -- the
     # chunks overlap each other's latency-bound phases and the workspace stays at 3 x 0.96 GB.
+    # `lap_times` batches up to here go through ltk_eval_alphas_host (measured: 247 / 256 / 285 us per call at
+    # 1 / 44 / 1,024 candidates against 284 / 289 / 302 us through the torch-staged route; from 8,192 on the
+    # single-threaded copy into the staging buffer makes it the slower one)
+    HOST_GRAPH_MAX = 2048
     WAVE = 65536  # measured against 75,776 (= 4 warps on every scheduler): 12.9 vs 13.6 ms for 2^20 candidates
     wave_lanes = 3
 
@@ -292,11 +296,23 @@ class LapTimeEvaluator:
         return out
 
     def lap_times(self, alphas):
-        """Host in, host out: numpy [B, n_alpha] -> numpy [B], through pinned staging buffers."""
-        torch = self.torch
+        """Host in, host out: numpy [B, n_alpha] -> numpy [B]."""
         a = np.ascontiguousarray(alphas, dtype=np.float64)
         if a.ndim == 1:
             a = a.reshape(1, -1)
+        B = a.shape[0]
+        if a.shape[1] != self.n_alpha:
+            raise ValueError(f"alphas must be [B, {self.n_alpha}]")
+        if 0 < B <= self.HOST_GRAPH_MAX:
+            # the optimiser loops' latency path: one native call, one CUDA graph per batch size
+            out = np.empty(B, dtype=np.float64)
+            _native.check(self.lib.ltk_eval_alphas_host(self._ctx, a.ctypes.data, B, out.ctypes.data), self._ctx)
+            return out
+        return self._lap_times_staged(a)
+
+    def _lap_times_staged(self, a):
+        """The torch route of `lap_times`: pinned staging tensors, the current stream, any batch size."""
+        torch = self.torch
         B = a.shape[0]
         if self._pinned is None or self._pinned.shape[0] < B:
             self._pinned = torch.empty((B, self.n_alpha), dtype=torch.float64).pin_memory()

@@ -479,3 +479,45 @@ def test_kernel_trace(buckmore):
     assert rows[0][2] == 0.0 and all(r[3] >= r[2] for r in rows)
     assert all(rows[i + 1][2] >= rows[i][3] - 1e-3 for i in range(len(rows) - 1))  # one stream: back to back
     assert ev.trace_read() == []  # reading switches tracing off
+
+
+def test_host_call_graph_path(buckmore, golden):
+    """ltk_eval_alphas_host (one CUDA graph per batch size up to 16,384 candidates; what `lap_times` uses for small batches):
+    bit-identical to the oracle and to the stream-launched route for every batch size, across more sizes than
+    the graph cache holds, on repeated calls with new values, and after the setters that invalidate the
+    graphs (sampling density, sweep precision)."""
+    ev, co = buckmore
+    rng = np.random.default_rng(21)
+    sizes = [1, 2, 10, 31, 32, 33, 45, 132, 1000, 4097, 16384, 16385, 10, 1, 132]  # > 8 distinct, then repeats
+    for B in sizes:
+        a = rng.uniform(0.0, 0.99, (B, ev.n_alpha))
+        got = np.empty(B)
+        ltk._native.check(ev.lib.ltk_eval_alphas_host(ev._ctx, a.ctypes.data, B, got.ctypes.data), ev._ctx)
+        assert np.array_equal(got, ev._lap_times_staged(a))
+        assert np.array_equal(got, ev.lap_times(a))
+        check = min(B, 256)
+        assert np.array_equal(got[:check], co.lap_times(a[:check]))
+    # the same graph, new inputs each call (the optimiser loops' pattern)
+    for _ in range(5):
+        a = rng.uniform(0.0, 0.99, (45, ev.n_alpha))
+        assert np.array_equal(ev.lap_times(a), co.lap_times(a))
+    # a one-dimensional alpha vector is one candidate (calcMinTime's calling convention)
+    assert np.array_equal(ev.lap_times(a[0]), co.lap_times(a[:1]))
+
+    g = golden("buckmore_tbr18_bayes_ns2501")
+    ev2, _ = make("buckmore_tbr18_bayes")
+    a = rng.uniform(0.0, 0.99, (45, ev2.n_alpha))
+    before = ev2.lap_times(a)
+    ev2.set_ns(int(g["ns"]))
+    tj, width, vj, mode = case_setup("buckmore_tbr18_bayes")
+    co2 = c_oracle.COracle(OracleTrack(tj, width), load_vehicle(vj), mode, int(g["ns"]), device_sum_order=True)
+    after = ev2.lap_times(a)
+    assert np.array_equal(after, co2.lap_times(a)) and not np.array_equal(after, before)
+    ev2.set_sweep_precision(32)
+    approx = ev2.lap_times(a)
+    assert not np.array_equal(approx, after) and np.max(np.abs(approx / after - 1.0)) < 1e-4
+    ev2.set_sweep_precision(64)
+    assert np.array_equal(ev2.lap_times(a), after)
+    with pytest.raises(ValueError):
+        ev2.lap_times(np.zeros((3, ev2.n_alpha + 1)))
+    ev2.close()
