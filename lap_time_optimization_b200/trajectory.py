@@ -123,6 +123,28 @@ class Trajectory:
 
         return self._minimise(obj)
 
+    def minimise_optimal_compromise(self, eps_min=0, eps_max=0.2):
+        """The compromise weight with the lowest lap time: a bounded scalar search over `eps`, each probe
+        one `minimise_compromise` run followed by one lap-time evaluation of its path; leaves `epsilon`,
+        `epsilon_history` ([eps, lap time] rows, one row stays one-dimensional as in the reference) and
+        the path of the best weight (trajectory.py:99-126)."""
+        from scipy.optimize import minimize_scalar
+
+        probes = []
+
+        def fun(eps):
+            self.minimise_compromise(eps)
+            lap = float(self.evaluator.lap_times(self.alphas)[0])
+            probes.append([eps, lap])
+            return lap
+
+        t0 = time.time()
+        res = minimize_scalar(fun=fun, method="bounded", bounds=(eps_min, eps_max))
+        self.epsilon_history = np.array(probes[0]) if len(probes) == 1 else np.array(probes)
+        self.epsilon = res.x
+        self.minimise_compromise(self.epsilon)
+        return time.time() - t0
+
     def minimise_lap_time(self):
         """Generate a path that directly minimises lap time (trajectory.py:128-146)."""
         return self._minimise(self.evaluator.lap_times)

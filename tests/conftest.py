@@ -18,7 +18,8 @@ def pytest_configure(config):
 
 def golden_cases():
     names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-    return [n for n in names if not n.startswith("objectives_")]  # objectives_*: tools/make_golden_objectives.py
+    # objectives_*: tools/make_golden_objectives.py, compromise_*: tools/make_golden_compromise.py
+    return [n for n in names if not n.startswith(("objectives_", "compromise_"))]
 
 
 def case_setup(name):

@@ -4,6 +4,8 @@
   (c) size-independent properties (idempotence, permutation / chunking invariance, ragged batches).
 Tolerances (fp64): CUDA == C oracle exactly; lap vs reference <= 1e-9 relative on the BASELINE
 populations except the documented friction-circle noise floor (DESIGN.md "Parity")."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -521,3 +523,41 @@ def test_host_call_graph_path(buckmore, golden):
     with pytest.raises(ValueError):
         ev2.lap_times(np.zeros((3, ev2.n_alpha + 1)))
     ev2.close()
+
+
+def test_minimise_optimal_compromise_follows_reference():
+    """`Trajectory.minimise_optimal_compromise` (trajectory.py:99-126) against a run of the unmodified reference
+    (tests/golden/compromise_buckmore.npz, tools/make_golden_compromise.py).  The bounded scalar search probes the
+    same weights as long as the lap times order the same way.  Each probe is an L-BFGS-B run on finite-difference
+    gradients (step 1e-8 on an objective known to 1e-11): where it stops moves with rounding, so what is compared is
+    the compromise objective it reached, and the lap times only loosely (the reference's own probes scatter by
+    0.08 s around the optimum: 38.76 .. 38.84 s for weights 0.0075 .. 0.0090)."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "compromise_buckmore.npz"))
+    track = ltk.Track(ltk.data_path("tracks/buckmore.json"), track_width=float(g["width"]), quiet=True)
+    T = ltk.Trajectory(track, ltk.load_vehicle(ltk.data_path("vehicles/tbr18.json")))
+    assert T.ns == int(g["ns"])
+    reached, inner = [], T.minimise_compromise
+
+    def logged(eps):
+        spent = inner(eps)
+        k, d = T.evaluator.curvature_objectives(np.asarray(T.alphas)[None, :])
+        reached.append([eps, k[0], d[0]])
+        return spent
+
+    T.minimise_compromise = logged
+    spent = T.minimise_optimal_compromise()
+    hist, ref = np.atleast_2d(T.epsilon_history), g["history"]
+    reached, ref_reached = np.array(reached), g["reached"]
+    lead = 6  # golden-section probes before the parabolic steps start to depend on the noise
+    cost = lambda r: (1 - r[:, 0]) * r[:, 1] + r[:, 0] * r[:, 2]  # noqa: E731
+    gap = cost(reached[:lead]) / cost(ref_reached[:lead]) - 1.0
+    print(f"optimal compromise: {spent:.1f} s, {len(hist)} probes, epsilon {T.epsilon:.6f} (reference {float(g['epsilon']):.6f}), "
+          f"lap {T.lap_time():.4f} (reference {float(g['lap']):.4f}); objective reached vs reference {gap}; "
+          f"lap at the probes {hist[:lead, 1]} vs {ref[:lead, 1]}")
+    assert np.allclose(hist[:lead, 0], ref[:lead, 0], rtol=0, atol=1e-12)
+    assert np.max(np.abs(gap)) < 1e-3
+    assert np.max(np.abs(hist[:lead, 1] - ref[:lead, 1])) < 0.3
+    assert 0.0 < T.epsilon < 0.02
+    assert abs(T.lap_time() - float(g["lap"])) < 0.2
+    assert abs(hist[:, 1].min() - ref[:, 1].min()) < 0.1
+    assert np.all((np.asarray(T.alphas) >= 0.0) & (np.asarray(T.alphas) <= 1.0))
