@@ -131,6 +131,23 @@ def test_full_size_population_bit_exact_and_topk(veh):
     ev.close()
 
 
+@pytest.mark.parametrize("mode", ["bayes", "full"])
+@pytest.mark.parametrize("veh", ["tbr18", "mx5"])
+@pytest.mark.parametrize("track", ["buckmore", "clay", "gyg", "whilton"])
+def test_every_track_vehicle_and_mode_bit_exact(track, veh, mode):
+    """Every data set the reference ships (data/tracks x data/vehicles), both alpha parameterisations: a
+    4,096-candidate population equals the C oracle bit for bit; the top-10 equals a stable host sort."""
+    ev, co = make(f"{track}_{veh}_{mode}")
+    a = np.random.default_rng(len(track) * 131 + len(veh) * 17 + len(mode)).uniform(0.0, 0.99, (4096, ev.n_alpha))
+    d_lap = ev.lap_times_device(torch.as_tensor(a).cuda())
+    laps, ref = d_lap.cpu().numpy(), co.lap_times(a)
+    assert np.array_equal(laps, ref) and np.isfinite(laps).all()
+    best, idx = ev.topk(d_lap, 10)
+    o_idx, o_best = top_k(list(ref), 10)
+    assert np.array_equal(idx, o_idx) and np.array_equal(best, o_best)
+    ev.close()
+
+
 def test_reference_port_sample_within_tolerance(buckmore):
     """End to end against the reference-equivalent Python port on fresh random candidates."""
     from oracle.reference_port import OracleEvaluator
