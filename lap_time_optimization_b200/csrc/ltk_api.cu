@@ -141,6 +141,10 @@ VehDev make_vehdev(const ltk_vehicle& v)
         engine_nonneg = (v.e0 >= 0.0);
     }
     if (!engine_nonneg) d.k_span_hi = 0u;  // never take the regular path (it assumes accel >= 0)
+    // the regular path also assumes mu g / k, f^2 - f_lat^2 and 2 F / m stay far from the ends of the exponent
+    // range for every k in the window: true for any physical vehicle, checked so that an odd one is only slow
+    auto moderate = [](double x) { return x >= 0x1p-100 && x <= 0x1p100; };
+    if (!moderate(v.mu_g) || !moderate(v.f_max) || !moderate(v.mass)) d.k_span_hi = 0u;
     d.lut_shift = 0; d.lut_base = 0; d.lut_top = -1;
     return d;
 }
@@ -232,7 +236,10 @@ WsLayout ws_layout(int ns, int N, long long B, bool dumps)
     w.Bp = round_up(B < 1 ? 1 : B, 32);  // multiple of TILE and of the warp size
     size_t rows = (size_t)(ns - 1);
     size_t arr = rows * (size_t)w.Bp * sizeof(double);
-    size_t off = 0;
+    // K23's look-ahead loads are unconditional: up to 2 * FUSED_UNROLL rows before the first / after the last
+    // row of a tile are read (never used).  Inside the arrays that is a neighbouring tile; the front of the
+    // curvature array gets SWEEP_SLACK bytes, the staging array is followed by the small per-candidate arrays.
+    size_t off = SWEEP_SLACK;
     w.kap_off = off; off += arr;
     w.vacc_off = off; off += arr;
     w.len_off = off; off += (size_t)w.Bp * sizeof(double);

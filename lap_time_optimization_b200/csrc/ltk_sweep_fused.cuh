@@ -34,6 +34,10 @@ namespace ltk {
 
 constexpr int FUSED_THREADS = 64;
 constexpr int FUSED_UNROLL = 2;
+// bytes of readable memory the workspace keeps in front of the curvature array (ws_layout): the look-ahead
+// loads of the sweep run 2 * FUSED_UNROLL rows past the rows a chain uses, unconditionally
+constexpr size_t SWEEP_SLACK = 1024;
+static_assert(SWEEP_SLACK >= 2 * FUSED_UNROLL * TILE * sizeof(double), "look-ahead rows must fit the slack");
 constexpr unsigned FULL_MASK = 0xffffffffu;
 
 struct FusedArgs {
@@ -290,7 +294,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 8) k23_sweep(FusedArgs a, VehDe
     const double* kbp = a.kap + base + (size_t)(n - 1) * P;    // backward cursor: row n-1 downwards
     double* sfp = a.stage + base + P;
     double* sbp = a.stage + base + (size_t)(n - 1) * P;
-    size_t rf = base + P, rb = base + (size_t)(n - 1) * P;     // same cursors as offsets (dumps)
+#define LTK_RF ((size_t)(kfp - a.kap))  // the cursors as element offsets (dump arrays share the layout)
+#define LTK_RB ((size_t)(kbp - a.kap))
 
     // ---- generic single step (library operators, reference branch structure); used for tails, the
     //      middle row, irregular blocks and dumps ----------------------------------------------------
@@ -312,39 +317,44 @@ __global__ void __launch_bounds__(FUSED_THREADS, 8) k23_sweep(FusedArgs a, VehDe
         if (phase == 1) {
             *sfp = va;
             *sbp = vd;
-            if (dump) { a.vacc_d[rf] = va; a.vdec_d[rb] = vd; }
+            if (dump) { a.vacc_d[LTK_RF] = va; a.vdec_d[LTK_RB] = vd; }
         } else {
             double o = *sfp;  // v_dec parked by the backward chain
             double v = (va < o) ? va : o;
             c.lap_f = c.lap_f + c.ds_f / v;
-            if (dump) { a.vacc_d[rf] = va; a.vmin_d[rf] = v; }
+            if (dump) { a.vacc_d[LTK_RF] = va; a.vmin_d[LTK_RF] = v; }
             o = *sbp;  // v_acc parked by the forward chain
             v = (o < vd) ? o : vd;
             c.lap_b = c.lap_b + ds_b / v;
-            if (dump) { a.vdec_d[rb] = vd; a.vmin_d[rb] = v; }
+            if (dump) { a.vdec_d[LTK_RB] = vd; a.vmin_d[LTK_RB] = v; }
         }
-        kfp += P; sfp += P; rf += P;
-        kbp -= P; sbp -= P; rb -= P;
+        kfp += P; sfp += P;
+        kbp -= P; sbp -= P;
     };
+
+    // The regular path keeps the chain state regular (v^2 = min(w + a ds, mu g / k) with k inside the window
+    // and a >= 0), so the state is only re-examined after steps on the library-operator path.
+    auto chains_regular = [&]() {
+        return is_regular(c.vf) && kappa_regular(V, c.kf) && is_regular(c.vb) && kappa_regular(V, c.kb);
+    };
+    bool state_ok = chains_regular();
 
     // ---- phase 1 -----------------------------------------------------------------------------------
     int t = 0;  // steps done in this phase
     if (!dump) {
         double fc[U], fn[U], bc[U], bn[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            bool in = (u < h);
-            fc[u] = in ? kfp[(size_t)u * P] : 1.0;
-            bc[u] = in ? *(kbp - (size_t)u * P) : 1.0;
+        for (int u = 0; u < U; ++u) {  // look-ahead loads are unconditional: see SWEEP_SLACK
+            fc[u] = kfp[(size_t)u * P];
+            bc[u] = *(kbp - (size_t)u * P);
         }
         for (; t + U <= h; t += U) {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                bool in = (t + U + u < h);
-                fn[u] = in ? kfp[(size_t)(U + u) * P] : 1.0;
-                bn[u] = in ? *(kbp - (size_t)(U + u) * P) : 1.0;
+                fn[u] = kfp[(size_t)(U + u) * P];
+                bn[u] = *(kbp - (size_t)(U + u) * P);
             }
-            bool regular = is_regular(c.vf) && kappa_regular(V, c.kf) && is_regular(c.vb) && kappa_regular(V, c.kb);
+            bool regular = state_ok;
 #pragma unroll
             for (int u = 0; u < U; ++u) regular = regular && kappa_regular(V, fc[u]) && kappa_regular(V, bc[u]);
             const bool nowrap = (c.qf + U < n) && (c.qb >= U);
@@ -352,11 +362,12 @@ __global__ void __launch_bounds__(FUSED_THREADS, 8) k23_sweep(FusedArgs a, VehDe
             if (all_regular) {
                 if (__all_sync(FULL_MASK, nowrap)) fused_block<KIND, ENG, 1, false>(V, S, c, fc, bc, fc, bc, sfp, sbp);
                 else fused_block<KIND, ENG, 1, true>(V, S, c, fc, bc, fc, bc, sfp, sbp);
-                kfp += (size_t)U * P; sfp += (size_t)U * P; rf += (size_t)U * P;
-                kbp -= (size_t)U * P; sbp -= (size_t)U * P; rb -= (size_t)U * P;
+                kfp += (size_t)U * P; sfp += (size_t)U * P;
+                kbp -= (size_t)U * P; sbp -= (size_t)U * P;
             } else {  // zero / inf / nan curvature somewhere in this block of this warp
 #pragma unroll 1
                 for (int u = 0; u < U; ++u) step_safe(1);
+                state_ok = chains_regular();
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) { fc[u] = fn[u]; bc[u] = bn[u]; }
@@ -376,34 +387,33 @@ __global__ void __launch_bounds__(FUSED_THREADS, 8) k23_sweep(FusedArgs a, VehDe
         double vd = backward_step<KIND, true>(V, c.vb, c.kb, vl, ds_b);
         double v = (va < vd) ? va : vd;
         term_mid = ds_b / v;
-        if (dump) { a.vacc_d[rf] = va; a.vdec_d[rf] = vd; a.vmin_d[rf] = v; }
+        if (dump) { a.vacc_d[LTK_RF] = va; a.vdec_d[LTK_RF] = vd; a.vmin_d[LTK_RF] = v; }
         c.vf = va; c.kf = kc; c.vb = vd; c.kb = kc;
-        kfp += P; sfp += P; rf += P;
-        kbp -= P; sbp -= P; rb -= P;
+        kfp += P; sfp += P;
+        kbp -= P; sbp -= P;
     }
 
     // ---- phase 2 -----------------------------------------------------------------------------------
+    state_ok = chains_regular();  // the middle row ran on the library-operator path
     t = 0;
     if (!dump) {
         double fc[U], fn[U], bc[U], bn[U], fo[U], fon[U], bo[U], bon[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            bool in = (u < h);
-            fc[u] = in ? kfp[(size_t)u * P] : 1.0;
-            fo[u] = in ? sfp[(size_t)u * P] : 1.0;
-            bc[u] = in ? *(kbp - (size_t)u * P) : 1.0;
-            bo[u] = in ? *(sbp - (size_t)u * P) : 1.0;
+            fc[u] = kfp[(size_t)u * P];
+            fo[u] = sfp[(size_t)u * P];
+            bc[u] = *(kbp - (size_t)u * P);
+            bo[u] = *(sbp - (size_t)u * P);
         }
         for (; t + U <= h; t += U) {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                bool in = (t + U + u < h);
-                fn[u] = in ? kfp[(size_t)(U + u) * P] : 1.0;
-                fon[u] = in ? sfp[(size_t)(U + u) * P] : 1.0;
-                bn[u] = in ? *(kbp - (size_t)(U + u) * P) : 1.0;
-                bon[u] = in ? *(sbp - (size_t)(U + u) * P) : 1.0;
+                fn[u] = kfp[(size_t)(U + u) * P];
+                fon[u] = sfp[(size_t)(U + u) * P];
+                bn[u] = *(kbp - (size_t)(U + u) * P);
+                bon[u] = *(sbp - (size_t)(U + u) * P);
             }
-            bool regular = is_regular(c.vf) && kappa_regular(V, c.kf) && is_regular(c.vb) && kappa_regular(V, c.kb);
+            bool regular = state_ok;
 #pragma unroll
             for (int u = 0; u < U; ++u)
                 regular = regular && kappa_regular(V, fc[u]) && kappa_regular(V, bc[u]) && is_regular(fo[u]) && is_regular(bo[u]);
@@ -412,11 +422,12 @@ __global__ void __launch_bounds__(FUSED_THREADS, 8) k23_sweep(FusedArgs a, VehDe
             if (all_regular) {
                 if (__all_sync(FULL_MASK, nowrap)) fused_block<KIND, ENG, 2, false>(V, S, c, fc, bc, fo, bo, sfp, sbp);
                 else fused_block<KIND, ENG, 2, true>(V, S, c, fc, bc, fo, bo, sfp, sbp);
-                kfp += (size_t)U * P; sfp += (size_t)U * P; rf += (size_t)U * P;
-                kbp -= (size_t)U * P; sbp -= (size_t)U * P; rb -= (size_t)U * P;
+                kfp += (size_t)U * P; sfp += (size_t)U * P;
+                kbp -= (size_t)U * P; sbp -= (size_t)U * P;
             } else {  // zero / inf / nan curvature somewhere in this block of this warp
 #pragma unroll 1
                 for (int u = 0; u < U; ++u) step_safe(2);
+                state_ok = chains_regular();
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) { fc[u] = fn[u]; bc[u] = bn[u]; fo[u] = fon[u]; bo[u] = bon[u]; }
@@ -425,6 +436,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 8) k23_sweep(FusedArgs a, VehDe
 #pragma unroll 1
     for (; t < h; ++t) step_safe(2);
 
+#undef LTK_RF
+#undef LTK_RB
     double lap = c.lap_f + c.lap_b;
     if (has_mid) lap = lap + term_mid;
     if (b < a.B) a.lap[b] = lap + term0;
