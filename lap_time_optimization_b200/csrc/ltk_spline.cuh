@@ -203,14 +203,16 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a)
     const long long b0 = (long long)blockIdx.x * G;
 
     // ---- L: control points from the alphas; knots and second derivatives from K1a ----------------------
-    for (int idx = tid; idx < NG; idx += T) {
-        const int g = idx / N, j = idx - g * N;  // j fastest: a candidate's alpha row is contiguous
+    {   // T / G threads per candidate, j fastest: a candidate's alpha row is contiguous (no division by N)
+        const int g = tid / CPT;
         long long b = b0 + g;
         b = (b < a.B) ? b : a.B - 1;             // padding lanes repeat the last candidate
-        double x, y;
-        control_point(a, b, j, x, y);
-        PX[j * G + g] = x;
-        PY[j * G + g] = y;
+        for (int j = tid - g * CPT; j < N; j += CPT) {
+            double x, y;
+            control_point(a, b, j, x, y);
+            PX[j * G + g] = x;
+            PY[j * G + g] = y;
+        }
     }
     for (int idx = tid; idx < NG + G; idx += T) {
         const int j = idx / G, g = idx - j * G;
