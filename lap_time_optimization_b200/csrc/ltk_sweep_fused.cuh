@@ -37,7 +37,18 @@ constexpr int FUSED_UNROLL = 2;
 // bytes of readable memory the workspace keeps in front of the curvature array (ws_layout): the look-ahead
 // loads of the sweep run 2 * FUSED_UNROLL rows past the rows a chain uses, unconditionally
 constexpr size_t SWEEP_SLACK = 1024;
-static_assert(SWEEP_SLACK >= 2 * FUSED_UNROLL * TILE * sizeof(double), "look-ahead rows must fit the slack");
+#ifndef LTK_SWEEP_PREFETCH
+#define LTK_SWEEP_PREFETCH 2  // blocks of FUSED_UNROLL rows fetched into L1 ahead of the register look-ahead (0: none)
+#endif
+static_assert(SWEEP_SLACK >= (2 + LTK_SWEEP_PREFETCH) * FUSED_UNROLL * TILE * sizeof(double),
+              "look-ahead rows must fit the slack");
+
+// The register look-ahead is one block (FUSED_UNROLL rows) deep: more would cost registers the kernel does not
+// have.  A prefetch into L1 one block further ahead costs none: the register loads then hit L1.
+__device__ __forceinline__ void prefetch_l1(const double* p)
+{
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
 constexpr unsigned FULL_MASK = 0xffffffffu;
 
 struct FusedArgs {
@@ -353,6 +364,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, 8) k23_sweep(FusedArgs a, VehDe
             for (int u = 0; u < U; ++u) {
                 fn[u] = kfp[(size_t)(U + u) * P];
                 bn[u] = *(kbp - (size_t)(U + u) * P);
+                if (LTK_SWEEP_PREFETCH) {
+                    prefetch_l1(kfp + (size_t)((1 + LTK_SWEEP_PREFETCH) * U + u) * P);
+                    prefetch_l1(kbp - (size_t)((1 + LTK_SWEEP_PREFETCH) * U + u) * P);
+                }
             }
             bool regular = state_ok;
 #pragma unroll
@@ -412,6 +427,12 @@ __global__ void __launch_bounds__(FUSED_THREADS, 8) k23_sweep(FusedArgs a, VehDe
                 fon[u] = sfp[(size_t)(U + u) * P];
                 bn[u] = *(kbp - (size_t)(U + u) * P);
                 bon[u] = *(sbp - (size_t)(U + u) * P);
+                if (LTK_SWEEP_PREFETCH) {
+                    prefetch_l1(kfp + (size_t)((1 + LTK_SWEEP_PREFETCH) * U + u) * P);
+                    prefetch_l1(sfp + (size_t)((1 + LTK_SWEEP_PREFETCH) * U + u) * P);
+                    prefetch_l1(kbp - (size_t)((1 + LTK_SWEEP_PREFETCH) * U + u) * P);
+                    prefetch_l1(sbp - (size_t)((1 + LTK_SWEEP_PREFETCH) * U + u) * P);
+                }
             }
             bool regular = state_ok;
 #pragma unroll
