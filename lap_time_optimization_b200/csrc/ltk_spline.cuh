@@ -202,7 +202,16 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long b0 = (long long)blockIdx.x * G;
 
-    // ---- L: control points from the alphas; knots and second derivatives from K1a ----------------------
+    // ---- L: control points from the alphas; knots and second derivatives from K1a.  The hand-off loads of the
+    //      first round are issued before the control-point loads are consumed, so the two latencies overlap ----
+    double u_first = 0.0, rx_first = 0.0, ry_first = 0.0, len_first = 0.0;
+    const bool first_row = tid < NG + G, first_m = tid < NG;
+    if (first_row) u_first = a.knots[(size_t)(tid / G) * a.Bp + b0 + (tid % G)];
+    if (first_m) {
+        rx_first = a.mx[(size_t)(tid / G) * a.Bp + b0 + (tid % G)];
+        ry_first = a.my[(size_t)(tid / G) * a.Bp + b0 + (tid % G)];
+    }
+    if (tid < G) len_first = a.knots[(size_t)N * a.Bp + b0 + tid];
     {   // T / G threads per candidate, j fastest: a candidate's alpha row is contiguous (no division by N)
         const int g = tid / CPT;
         long long b = b0 + g;
@@ -214,7 +223,9 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a)
             PY[j * G + g] = y;
         }
     }
-    for (int idx = tid; idx < NG + G; idx += T) {
+    if (first_row) U[tid] = u_first;
+    if (first_m) { RX[tid] = rx_first; RY[tid] = ry_first; }
+    for (int idx = tid + T; idx < NG + G; idx += T) {
         const int j = idx / G, g = idx - j * G;
         U[idx] = a.knots[(size_t)j * a.Bp + b0 + g];
         if (j < N) {
@@ -222,7 +233,7 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a)
             RY[idx] = a.my[(size_t)j * a.Bp + b0 + g];
         }
     }
-    if (tid < G) LEN[tid] = a.knots[(size_t)N * a.Bp + b0 + tid];
+    if (tid < G) LEN[tid] = len_first;
     __syncthreads();
     // ---- C: per-interval coefficients  S'(t) = c1 + t (c2 + t h),  S''(t) = c2 + c3 t,  h = c3/2, and the
     //      first sample index of every interval: IB[j] = min{ i : fl(i*step) >= U[j] } ------------------
