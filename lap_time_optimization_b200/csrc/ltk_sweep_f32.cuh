@@ -23,6 +23,15 @@ namespace ltk {
 
 constexpr int F32_THREADS = 128;
 constexpr int F32_UNROLL = 4;
+#ifndef LTK_F32_PREFETCH
+#define LTK_F32_PREFETCH 1
+#endif
+constexpr bool F32_PREFETCH = LTK_F32_PREFETCH != 0;  // L1 prefetch one block ahead of the register look-ahead
+
+__device__ __forceinline__ void prefetch_l1_any(const void* p)
+{
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
 
 struct F32Args {
     const double* kap;   // [n][tile-blocked] rotated curvature (fp64, from K1b)
@@ -150,6 +159,13 @@ __global__ void __launch_bounds__(F32_THREADS) k23_f32(F32Args a, VehF32 V)
                 fn[u] = in ? kfp[(size_t)(U + u) * P] : (KT_)1;
                 bn[u] = in ? *(kbp - (size_t)(U + u) * P) : (KT_)1;
             }
+            if (F32_PREFETCH) {  // one 128-byte line holds two fp32 rows of a tile
+#pragma unroll
+                for (int u = 0; u < U; u += 2) {
+                    prefetch_l1_any(kfp + (size_t)(2 * U + u) * P);
+                    prefetch_l1_any(kbp - (size_t)(2 * U + u) * P);
+                }
+            }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 sfp[(size_t)u * P] = fwd((float)fc[u]);
@@ -192,6 +208,15 @@ __global__ void __launch_bounds__(F32_THREADS) k23_f32(F32Args a, VehF32 V)
                 bn[u] = in ? *(kbp - (size_t)(U + u) * P) : (KT_)1;
                 fon[u] = in ? sfp[(size_t)(U + u) * P] : 1.0f;
                 bon[u] = in ? *(sbp - (size_t)(U + u) * P) : 1.0f;
+            }
+            if (F32_PREFETCH) {
+#pragma unroll
+                for (int u = 0; u < U; u += 2) {
+                    prefetch_l1_any(kfp + (size_t)(2 * U + u) * P);
+                    prefetch_l1_any(kbp - (size_t)(2 * U + u) * P);
+                    prefetch_l1_any(sfp + (size_t)(2 * U + u) * P);
+                    prefetch_l1_any(sbp - (size_t)(2 * U + u) * P);
+                }
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
