@@ -56,6 +56,8 @@ def parse():
     p.add_argument("--sweep-bits", type=int, default=64, choices=[64, 32],
                    help="32 = the optional fp32 variant of the velocity sweeps (spline and curvature stay fp64)")
     p.add_argument("--lanes", type=int, default=3, help="populations in flight per GPU (1 = strictly one step at a time)")
+    p.add_argument("--e2e-slots", type=int, default=None,
+                   help="input/result buffer sets of the end-to-end pipeline (default 2 x lanes)")
     return p.parse_args()
 
 
@@ -282,11 +284,11 @@ def run_ours(args):
         checksum = 0.0
         for laps, best_h, idx_h in ev.stream_populations((pin_in[i % 4] for i in range(nsteps)), TOPK,
                                                          index_base=base, index_stride=0, finish=finish,
-                                                         lanes=LANES):
+                                                         lanes=LANES, slots=args.e2e_slots):
             checksum += float(best_h[0]) + float(laps[-1])  # results are consumed on the host
         return checksum
 
-    e2e_run(3)
+    e2e_run(max(3, (args.e2e_slots or 2 * LANES) + 1))  # every buffer set exists before the timed region
     barrier()
     t0e = time.perf_counter()
     e2e_run(args.steps)
@@ -328,7 +330,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * na * 8,
                     "d2h_bytes_per_step": B * 8 + TOPK * 16,
                     "pipeline": f"LapTimeEvaluator.stream_populations: {LANES} populations in flight, each on its own "
-                                "compute stream; uploads and downloads on two copy streams"},
+                                f"compute stream; uploads and downloads on two copy streams; {args.e2e_slots or 2 * LANES} buffer sets"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

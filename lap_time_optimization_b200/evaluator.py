@@ -324,16 +324,21 @@ class LapTimeEvaluator:
         torch.cuda.current_stream(self.device).synchronize()
         return self._pinned_out[:B].numpy().copy()
 
-    def stream_populations(self, populations, k=DEFAULT_TOPK, index_base=0, index_stride=None, finish=None, lanes=3):
+    def stream_populations(self, populations, k=DEFAULT_TOPK, index_base=0, index_stride=None, finish=None, lanes=3,
+                           slots=None):
         """Score a SEQUENCE of host populations with copies and kernels overlapped.
 
         `populations` yields float64 arrays [B, n_alpha]: pinned torch tensors are copied as they are,
         numpy arrays / pageable tensors go through a pinned staging buffer first.  `lanes` populations
         are in flight at a time, each on its own compute stream (see `lanes()`); one copy stream moves
         the next populations host->device and a second one the finished results device->host, so
-        uploads, kernels and downloads of different populations overlap.  Yields, in submission order,
-        one `(laps, best_laps, best_idx)` triple of numpy views per population; the views alias pinned
-        slot buffers and stay valid until `lanes` more results have been taken.  `finish(best, idx) ->
+        uploads, kernels and downloads of different populations overlap.  Input / result buffers come in
+        `slots` sets (default 2 x lanes): the host runs that many populations ahead of the results it hands
+        out, so a lane that finishes a population finds the next one already uploaded (with as many slots as
+        lanes the upload of population i could only be issued once population i - lanes had been taken,
+        and its lane idled through the copy).  Yields, in submission order, one `(laps, best_laps,
+        best_idx)` triple of numpy views per population; the views alias pinned slot buffers and stay
+        valid until the next result is requested.  `finish(best, idx) ->
         (best, idx)` runs on the population's compute stream after the local top-k (the multi-GPU
         all-gather + merge hooks in here).  Candidate j of population i gets the global index
         index_base + i*index_stride + j (index_stride defaults to the population size).  This is the
@@ -346,7 +351,7 @@ class LapTimeEvaluator:
         if getattr(self, "_copy_streams", None) is None:
             self._copy_streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
         copy_in, copy_out = self._copy_streams
-        nslot = len(pool)
+        nslot = max(len(pool), int(slots) if slots else 2 * len(pool))
         slots = [None] * nslot
         pending = []  # (slot index, B) in submission order
 
@@ -370,7 +375,7 @@ class LapTimeEvaluator:
         base = int(index_base)
         for i, pop in enumerate(populations):
             si = i % nslot
-            lane = pool[si]
+            lane = pool[i % len(pool)]
             if len(pending) == nslot:  # the slot about to be reused still holds an untaken result
                 yield take(pending.pop(0))
             t = pop if hasattr(pop, "is_pinned") else torch.from_numpy(np.ascontiguousarray(pop, dtype=np.float64))
