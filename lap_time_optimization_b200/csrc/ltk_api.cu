@@ -480,15 +480,18 @@ int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m
         f.ns = ctx->ns; f.B = B;
         unsigned gridf = (unsigned)((w.Bp + FUSED_THREADS - 1) / FUSED_THREADS);
         unsigned gridr = (unsigned)(w.Bp / 32);
-        // Small batches are latency-bound: one chain per thread, two warps per 32 candidates (K23r).
-        // From one resident wave upwards the two-chains-per-thread kernel is as fast or faster.
-        const bool roles = (ctx->sweep_mode == 2) || (ctx->sweep_mode == 0 && !dumps && B <= 16384);
+        // Small batches are latency-bound: one chain per thread, two warps per 32 candidates (K23r).  Both kernels'
+        // times step with the warps per scheduler (one two-chain warp per scheduler = 32 * 4 * SMs candidates, one
+        // "layer"): measured K23 / K23r at 8,192: 0.261 / 0.217 ms, 20,480: 0.289 / 0.263, 24,576: 0.290 / 0.265,
+        // 32,768: 0.292 / 0.318, 40,960: 0.398 / 0.399, 49,152: 0.398 / 0.479 -- one chain per thread up to one
+        // and a half layers (28,416 candidates on 148 SMs), two chains per thread above.
+        const long long layer = 32LL * 4 * ctx->sm_count;  // candidates in one two-chain warp per scheduler
+        const bool roles = (ctx->sweep_mode == 2) || (ctx->sweep_mode == 0 && !dumps && 2 * (long long)B <= 3 * layer);
         // A population that fills the two-chain kernel's warp slots unevenly -- e.g. 65,536 candidates =
         // 3.46 warps per scheduler, so most schedulers carry 4 warps and the rest idle a quarter of the
         // time -- is split: whole layers of one warp per scheduler go to the two-chain kernel, the
         // remainder to the one-chain kernel (half-size warps, two per 32 candidates) on a second stream,
         // so that the busiest schedulers carry 3.5 warps' worth instead of 4.
-        const long long layer = 32LL * 4 * ctx->sm_count;  // candidates in one warp per scheduler
         const long long whole = (w.Bp / layer) * layer;
         const long long rest = w.Bp - whole;
         const bool split = !roles && !dumps && ctx->sweep_mode == 0 && ctx->sweep_remainder && ctx->aux_stream &&

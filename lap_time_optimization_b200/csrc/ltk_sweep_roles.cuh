@@ -17,7 +17,7 @@
 // The two warps meet at one __syncthreads() between the halves (the parked rows cross over there).
 //
 // Measured (B200, Buckmore/TBR18): equal to the fused kernel at 65,536 candidates (0.56 ms), 17 % faster
-// at <= 16,384 (latency-bound: 0.217 vs 0.261 ms at 8,192), 13 % slower on multi-wave populations (a
+// at <= 28,416 (latency-bound: 0.217 vs 0.261 ms at 8,192, 0.265 vs 0.290 at 24,576), 13 % slower on multi-wave populations (a
 // forward step costs ~19 % more FP64-pipe time than a backward one, so the backward warp idles at the
 // barrier and at the end while holding its registers).  Swapping the chains between the warps at half
 // time was tried and does not help: the barrier makes each half take max(forward, backward) either way.

@@ -200,9 +200,9 @@ def test_stream_populations_matches_one_shot(buckmore):
     assert seen == len(pops)
 
 
-@pytest.mark.parametrize("B", [8192, 16384, 16385, 40000, 65537, 70001, 113665])
+@pytest.mark.parametrize("B", [8192, 16384, 16385, 28416, 28417, 40000, 65537, 70001, 113665])
 def test_small_and_large_batch_sweep_kernels_agree(buckmore, B):
-    """<= 16,384 candidates run the one-chain-per-thread sweep (K23r), larger batches the two-chain one:
+    """Up to 28,416 candidates (148 SMs) run the one-chain-per-thread sweep (K23r), larger batches the two-chain one:
     both must equal the oracle bit for bit on either side of the switch."""
     ev, co = buckmore
     a = np.random.default_rng(B).uniform(0.0, 0.99, (B, ev.n_alpha))
