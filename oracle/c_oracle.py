@@ -28,8 +28,8 @@ class _Vehicle(C.Structure):
 
 
 def build(force=False):
-    src = os.path.join(_HERE, "lap_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("lap_oracle.c", "fitpack_port.c", "Makefile")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-s", "-C", _HERE, "-B" if force else "--no-print-directory"])
     return _SO
 
@@ -53,6 +53,13 @@ def lib():
         _lib.lto_pairwise_sum.argtypes = [dp, C.c_long]
         _lib.lto_set_use_pow.argtypes = [C.c_int]
         _lib.lto_set_sum_mode.argtypes = [C.c_int]
+        _lib.lto_set_spline_mode.argtypes = [C.c_int]
+        _lib.lto_pow15.restype = C.c_double
+        _lib.lto_pow15.argtypes = [C.c_double]
+        _lib.fpk_clocur.restype = C.c_int
+        _lib.fpk_clocur.argtypes = [dp, dp, C.c_int, C.c_int, dp, dp]
+        _lib.fpk_splder.restype = None
+        _lib.fpk_splder.argtypes = [dp, C.c_int, dp, C.c_int, dp, C.c_int, dp, dp]
     return _lib
 
 
@@ -88,7 +95,7 @@ def vehicle_struct(veh):
 
 class COracle:
     def __init__(self, track: OracleTrack, vehicle, mode="bayes", ns=None, use_pow=False,
-                 device_sum_order=False):
+                 device_sum_order=False, spline="tridiagonal"):
         self.track, self.vehicle, self.mode = track, vehicle, mode
         self.ns = math.ceil(track.length) if ns is None else ns
         if mode == "bayes":
@@ -101,6 +108,9 @@ class COracle:
         self.N = self.left.shape[1]
         self.veh = vehicle_struct(vehicle)
         self.use_pow = use_pow
+        # "tridiagonal": classical cyclic-tridiagonal periodic spline (the default CUDA K1a);
+        # "fitpack": FITPACK's fpclos / splder arithmetic (oracle/fitpack_port.c), the reference's own bits
+        self.spline_mode = {"tridiagonal": 0, "fitpack": 1}[spline]
         # True / "fused": summation order of the fused sweep kernel (the default device path);
         # "split": order of the separate backward kernel (LTK_SWEEP=split)
         self.sum_mode = {False: 0, None: 0, True: 2, "fused": 2, "split": 1}[device_sum_order]
@@ -109,6 +119,7 @@ class COracle:
         L = lib()
         L.lto_set_use_pow(int(self.use_pow))
         L.lto_set_sum_mode(self.sum_mode)
+        L.lto_set_spline_mode(self.spline_mode)
         return L
 
     def lap_times(self, alphas, threads=None):
@@ -145,8 +156,37 @@ class COracle:
         return out
 
 
-def path_derivatives(px, py, ns):
-    """Closed-form periodic spline of one closed polygon (unique points; closure implied)."""
+def fitpack_spline(u, xy):
+    """FITPACK periodic interpolating cubic spline (oracle/fitpack_port.c): u [m] parameters, xy [idim][m]
+    points with xy[:, -1] == xy[:, 0].  Returns (t, [c_0, c_1, ...]) shaped like splprep's tck."""
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    xy = np.asarray(xy, dtype=np.float64)
+    idim, m = xy.shape
+    n = m + 6
+    t, c = np.zeros(n), np.zeros(idim * n)
+    pts = np.ascontiguousarray(xy.T.ravel())
+    assert lib().fpk_clocur(_p(u), _p(pts), m, idim, _p(t), _p(c)) == n
+    return t, [c[d * n:(d + 1) * n - 4].copy() for d in range(idim)]
+
+
+def fitpack_splder(t, c, nu, x):
+    """splev(x, (t, c, 3), der=nu) for one coordinate (oracle/fitpack_port.c splder)."""
+    t = np.ascontiguousarray(t, dtype=np.float64)
+    cc = np.zeros(t.size)
+    cc[:len(c)] = c
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y, wrk = np.zeros(x.size), np.zeros(t.size)
+    lib().fpk_splder(_p(t), t.size, _p(cc), nu, _p(x), x.size, _p(y), _p(wrk))
+    return y
+
+
+def pow15(x):
+    return lib().lto_pow15(float(x))
+
+
+def path_derivatives(px, py, ns, spline="tridiagonal"):
+    """Periodic spline of one closed polygon (unique points; closure implied)."""
+    lib().lto_set_spline_mode({"tridiagonal": 0, "fitpack": 1}[spline])
     px = np.ascontiguousarray(px, dtype=np.float64)
     py = np.ascontiguousarray(py, dtype=np.float64)
     n = ns - 1

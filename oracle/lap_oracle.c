@@ -54,6 +54,14 @@ static int g_use_pow = 0;
  * 1 and 2 exist for bit-for-bit checks of the device kernels. */
 static int g_sum_mode = 0;
 void lto_set_sum_mode(int m) { g_sum_mode = m; }
+/* 0: the classical cyclic-tridiagonal periodic spline below (what the default CUDA K1a solves);
+ * 1: FITPACK's own arithmetic (oracle/fitpack_port.c: fpclos Givens QR + splder), i.e. the bits
+ *    scipy.interpolate.splprep / splev produce for the reference (path.py:25, :51-54). */
+static int g_spline_mode = 0;
+void lto_set_spline_mode(int m) { g_spline_mode = m; }
+int fpk_clocur(const double *u, const double *x, int m, int idim, double *t, double *c);
+void fpk_splder(const double *t, int n, const double *c, int nu, const double *x, int m, double *y,
+                double *wrk);
 static volatile double g_two = 2.0; /* volatile: stops gcc folding pow(x, 2.0) into x*x */
 void lto_set_use_pow(int on) { g_use_pow = on; }
 static inline double sq(double x) { return g_use_pow ? pow(x, g_two) : x * x; }
@@ -299,6 +307,57 @@ static void spline_curvature(const double *u, const double *coef, int N, int ns,
     }
 }
 
+/* x**1.5 rounded to nearest: sqrt in double-double, product in double-double.  numpy evaluates
+ * `(dx**2 + dy**2) ** (3/2)` (path.py:58) with libm pow -- or, on AVX512 hosts, with its vendored SVML pow,
+ * which is off by one ulp in ~5 % of the arguments and cannot be restated; the correctly rounded value is
+ * what both approximate and what the CUDA kernel computes with the same four operations. */
+double lto_pow15(double x)
+{
+    double s = sqrt(x);
+    double r = fma(-s, s, x);  /* x - s*s exactly */
+    double e = r / (s + s);    /* sqrt(x) = s + e */
+    double p = x * s;
+    double pe = fma(x, s, -p); /* x*s = p + pe exactly */
+    return p + fma(x, e, pe);
+}
+
+/* FITPACK mode: knots = cumulative chord lengths of the closed polygon (path.py:11-14), periodic
+ * interpolating B-spline (path.py:25), derivative values at the samples (path.py:51-54), curvature in
+ * numpy's operation order (path.py:58, :61).  work: (N+1) + 2(N+1) + (N+7) + 2(N+7) + (N+7) + 4n doubles. */
+static double fitpack_curvature(const double *px, const double *py, int N, int ns, double *k, double *work,
+                                double *o_dx, double *o_dy, double *o_ddx, double *o_ddy)
+{
+    int m = N + 1, nk = m + 6, n = ns - 1;
+    double *u = work, *xy = u + m, *t = xy + 2 * m, *c = t + nk, *wrk = c + 2 * nk, *s = wrk + nk;
+    double *d1x = s + n, *d1y = d1x + n, *d2x = d1y + n;
+    u[0] = 0.0;
+    for (int j = 0; j < N; ++j) {
+        int jn = j + 1 == N ? 0 : j + 1;
+        double ex = px[jn] - px[j], ey = py[jn] - py[j];
+        u[j + 1] = u[j] + sqrt(ex * ex + ey * ey);
+        xy[2 * j] = px[j];
+        xy[2 * j + 1] = py[j];
+    }
+    xy[2 * N] = px[0];
+    xy[2 * N + 1] = py[0];
+    fpk_clocur(u, xy, m, 2, t, c);
+    double L = u[N], step = L / (double)(ns - 1);
+    for (int i = 0; i < n; ++i) s[i] = (double)i * step;
+    double *d2y = k; /* reuse the output as scratch for the last derivative */
+    fpk_splder(t, nk, c, 1, s, n, d1x, wrk);
+    fpk_splder(t, nk, c + nk, 1, s, n, d1y, wrk);
+    fpk_splder(t, nk, c, 2, s, n, d2x, wrk);
+    fpk_splder(t, nk, c + nk, 2, s, n, d2y, wrk);
+    for (int i = 0; i < n; ++i) {
+        double dx = d1x[i], dy = d1y[i], ddx = d2x[i], ddy = d2y[i];
+        if (o_dx) { o_dx[i] = dx; o_dy[i] = dy; o_ddx[i] = ddx; o_ddy[i] = ddy; }
+        double cross = dx * ddy - dy * ddx;
+        double n2 = dx * dx + dy * dy;
+        k[i] = fabs(cross / lto_pow15(n2));
+    }
+    return L;
+}
+
 /* ---- exported entry points (ctypes) ------------------------------------------------------------ */
 
 /* Sweeps only: one candidate, curvature supplied (e.g. the reference's own FITPACK curvature). */
@@ -328,6 +387,7 @@ static void *eval_range(void *arg)
     lto_job *jb = (lto_job *)arg;
     int N = jb->N, ns = jb->ns, n = ns - 1;
     double *px = (double *)malloc(sizeof(double) * (size_t)(2 * N + (N + 1) + 6 * N + 8 * N + 4 * n));
+    double *fw = g_spline_mode ? (double *)malloc(sizeof(double) * (size_t)(8 * (N + 7) + 4 * n)) : 0;
     double *py = px + N, *u = py + N, *coef = u + N + 1, *work = coef + 6 * N;
     double *k = work + 8 * N, *sw = k + n;
     for (long b = jb->b0; b < jb->b1; ++b) {
@@ -336,8 +396,13 @@ static void *eval_range(void *arg)
             px[j] = jb->left_xy[j] + a[j] * jb->diff_xy[j];
             py[j] = jb->left_xy[N + j] + a[j] * jb->diff_xy[N + j];
         }
-        double L = spline_build(px, py, N, u, coef, work);
-        spline_curvature(u, coef, N, ns, L, k, 0, 0, 0, 0);
+        double L;
+        if (g_spline_mode) {
+            L = fitpack_curvature(px, py, N, ns, k, fw, 0, 0, 0, 0);
+        } else {
+            L = spline_build(px, py, N, u, coef, work);
+            spline_curvature(u, coef, N, ns, L, k, 0, 0, 0, 0);
+        }
         int d = (b == jb->dump_index);
         jb->lap[b] = sweeps_one(jb->veh, k, ns, L, 1, d ? jb->o_vlocal : 0, d ? jb->o_vacc : 0,
                                 d ? jb->o_vdec : 0, d ? jb->o_v : 0, sw);
@@ -347,6 +412,7 @@ static void *eval_range(void *arg)
         }
     }
     free(px);
+    free(fw);
     return 0;
 }
 
@@ -376,10 +442,15 @@ int lto_path(const double *px, const double *py, int N, int ns, double *o_length
              double *o_dx, double *o_dy, double *o_ddx, double *o_ddy)
 {
     if (N < 3 || ns < 3) return -1;
-    double *u = (double *)malloc(sizeof(double) * (size_t)((N + 1) + 6 * N + 8 * N));
+    double *u = (double *)malloc(sizeof(double) * (size_t)((N + 1) + 6 * N + 8 * N + 8 * (N + 7) + 4 * ns));
     double *coef = u + N + 1, *work = coef + 6 * N;
-    double L = spline_build(px, py, N, u, coef, work);
-    spline_curvature(u, coef, N, ns, L, o_k, o_dx, o_dy, o_ddx, o_ddy);
+    double L;
+    if (g_spline_mode) {
+        L = fitpack_curvature(px, py, N, ns, o_k, work + 8 * N, o_dx, o_dy, o_ddx, o_ddy);
+    } else {
+        L = spline_build(px, py, N, u, coef, work);
+        spline_curvature(u, coef, N, ns, L, o_k, o_dx, o_dy, o_ddx, o_ddy);
+    }
     if (o_length) *o_length = L;
     free(u);
     return 0;

@@ -102,3 +102,84 @@ def test_topk_stable():
     laps = [3.0, 1.0, 2.0, 1.0, 5.0, 2.0]
     idx, best = top_k(laps, 4)
     assert list(idx) == [1, 3, 2, 5] and list(best) == [1.0, 1.0, 2.0, 2.0]
+
+
+# ---- FITPACK-faithful spline (oracle/fitpack_port.c) ------------------------------------------------
+def _closed_polygon(rng, m):
+    th = np.sort(rng.uniform(0, 2 * np.pi, m - 1))
+    r = rng.uniform(50, 120, m - 1)
+    pts = np.array([r * np.cos(th), r * np.sin(th)])
+    pts = np.concatenate([pts, pts[:, :1]], axis=1)
+    u = np.append(0, np.cumsum(np.linalg.norm(np.diff(pts, axis=1), axis=0)))
+    return u, pts
+
+
+def test_fitpack_port_equals_live_scipy():
+    """fpclos (s = 0, per = 1) and splder restated in C against the installed SciPy, bit for bit:
+    the call the reference makes at path.py:25 and path.py:51-54."""
+    from scipy.interpolate import splev, splprep
+
+    rng = np.random.default_rng(11)
+    for trial in range(60):
+        m = int(rng.integers(6, 160))
+        u, pts = _closed_polygon(rng, m)
+        (t, c, k), _ = splprep(pts.copy(), u=u, k=3, s=0, per=1)
+        t2, c2 = c_oracle.fitpack_spline(u, pts)
+        assert np.array_equal(t, t2)
+        assert np.array_equal(c[0], c2[0]) and np.array_equal(c[1], c2[1])
+        x = np.linspace(0, u[-1], 401)[:-1]
+        for nu in (0, 1, 2):
+            ys = splev(x, (t, c, k), der=nu)
+            for d in range(2):
+                assert np.array_equal(ys[d], c_oracle.fitpack_splder(t2, c2[d], nu, x)), (trial, nu, d)
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_fitpack_port_equals_reference_spline(name, golden):
+    """Same check against what the unmodified reference held in Path.spline (tools/make_golden.py)."""
+    g = golden(name)
+    for i in range(int(g["n_profiles"])):
+        t2, c2 = c_oracle.fitpack_spline(g["prof_dists"][i], g["prof_controls"][i])
+        assert np.array_equal(t2, g["prof_tck_t"][i])
+        assert np.array_equal(c2[0], g["prof_tck_cx"][i]) and np.array_equal(c2[1], g["prof_tck_cy"][i])
+        x = g["prof_s"][i][:-1]
+        for key, d, nu in (("dx", 0, 1), ("dy", 1, 1), ("ddx", 0, 2), ("ddy", 1, 2)):
+            assert np.array_equal(c_oracle.fitpack_splder(t2, c2[d], nu, x), g["prof_" + key][i]), key
+
+
+def test_pow15_is_correctly_rounded():
+    """x**1.5 by two double-double steps against exact integer arithmetic."""
+    from fractions import Fraction
+    from math import isqrt
+
+    rng = np.random.default_rng(5)
+    for x in np.concatenate([rng.uniform(0.3, 3.0, 1500), rng.uniform(1e-3, 1e3, 500)]):
+        x = float(x)
+        got = c_oracle.pow15(x)
+        f = Fraction(x) ** 3
+        root = Fraction(isqrt((f.numerator << 600) // f.denominator), 1 << 300)  # sqrt(x^3), 300 bits
+        cands = [got, float(np.nextafter(got, np.inf)), float(np.nextafter(got, -np.inf))]
+        assert min(cands, key=lambda v: abs(Fraction(v) - root)) == got
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_c_fitpack_mode_reproduces_reference(name, golden):
+    """Whole path with FITPACK's arithmetic.  Against the reference on numpy's baseline dispatch (libm
+    pow) the laps are bit-equal on nearly every candidate; against the reference on an AVX512 host (numpy's
+    SVML pow: one ulp off in ~5 % of the curvature samples) they carry that host's own spread."""
+    g = golden(name)
+    co = _c(name, int(g["ns"]), spline="fitpack", use_pow=True)
+    laps = co.lap_times(g["alphas"])
+    rel_base = rel_err(laps, g["laps_base"])
+    rel_host = rel_err(laps, g["laps"])
+    spread = rel_err(g["laps_base"], g["laps"]).max()  # the reference against itself
+    assert (rel_base == 0).mean() >= 0.8, (rel_base == 0).mean()
+    assert rel_base.max() <= 1e-10
+    assert rel_host.max() <= max(1e-9, 2 * spread)
+    for i in range(int(g["n_profiles"])):
+        pr = co.profile(g["alphas"][i])
+        assert pr["length"] == g["prof_length"][i]
+        kb = g["prof_k_base"][i]
+        assert (pr["k"] != kb).mean() <= 0.005  # libm pow is not always correctly rounded either
+        assert np.max(np.abs(pr["k"] - kb) / kb) <= 2.3e-16
+        assert np.max(np.abs(pr["k"] - g["prof_k"][i]) / kb) <= 4.5e-16
