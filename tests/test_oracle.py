@@ -181,5 +181,5 @@ def test_c_fitpack_mode_reproduces_reference(name, golden):
         assert pr["length"] == g["prof_length"][i]
         kb = g["prof_k_base"][i]
         assert (pr["k"] != kb).mean() <= 0.005  # libm pow is not always correctly rounded either
-        assert np.max(np.abs(pr["k"] - kb) / kb) <= 2.3e-16
-        assert np.max(np.abs(pr["k"] - g["prof_k"][i]) / kb) <= 4.5e-16
+        assert np.all(np.abs(pr["k"] - kb) <= np.spacing(kb))  # one ulp where they differ
+        assert np.all(np.abs(pr["k"] - g["prof_k"][i]) <= 2 * np.spacing(kb))
