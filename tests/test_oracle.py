@@ -181,5 +181,7 @@ def test_c_fitpack_mode_reproduces_reference(name, golden):
         assert pr["length"] == g["prof_length"][i]
         kb = g["prof_k_base"][i]
         assert (pr["k"] != kb).mean() <= 0.005  # libm pow is not always correctly rounded either
-        assert np.all(np.abs(pr["k"] - kb) <= np.spacing(kb))  # one ulp where they differ
-        assert np.all(np.abs(pr["k"] - g["prof_k"][i]) <= 2 * np.spacing(kb))
+        ulp = np.spacing(np.maximum(pr["k"], kb))
+        # one ulp of the power where they differ = up to two ulp of the quotient across a binade
+        assert np.all(np.abs(pr["k"] - kb) <= 2 * ulp)
+        assert np.all(np.abs(pr["k"] - g["prof_k"][i]) <= 3 * ulp)
