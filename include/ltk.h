@@ -75,6 +75,23 @@ int ltk_set_ns(ltk_ctx *ctx, int ns);
  * Affects ltk_eval_alphas / ltk_eval_controls; ltk_profile always uses fp64. */
 int ltk_set_sweep_precision(ltk_ctx *ctx, int bits);
 
+/* Spline arithmetic (Path.__init__ / Path.curvature, path.py:25, :51-61).  Both modes build the periodic
+ * interpolating cubic spline through the control points with chord-length knots; they differ in how.
+ *   LTK_SPLINE_TRIDIAGONAL (default): cyclic tridiagonal solve for the second derivatives (Thomas +
+ *       Sherman-Morrison), Horner evaluation.  Curvature agrees with SciPy's to ~1e-13 of its maximum; TBR18's
+ *       friction-circle cancellation (vehicle.py:29-35) turns that into lap-time differences of median 2e-11,
+ *       but > 1e-9 on about one candidate in 4,000.
+ *   LTK_SPLINE_FITPACK: SciPy FITPACK's own algorithm and operation order -- clocur/fpclos (Givens QR of the
+ *       periodic collocation matrix, fpbacp) for splprep(k=3, s=0, per=1), splder/fpbspl for splev(der=1|2):
+ *       B-spline coefficients and derivative values bit-equal to SciPy's, curvature with a correctly rounded
+ *       x**1.5 (numpy's pow is libm's, or an SVML routine one ulp off on AVX512 hosts).  Lap times then equal
+ *       the reference's bit for bit on most candidates and stay within 1e-9 on every one.  Costs ~4 KB more
+ *       workspace per candidate (ask ltk_workspace_bytes AFTER setting the mode) and a slower K1. */
+#define LTK_SPLINE_TRIDIAGONAL 0
+#define LTK_SPLINE_FITPACK 1
+int ltk_set_spline_mode(ltk_ctx *ctx, int mode);
+int ltk_spline_mode(const ltk_ctx *ctx);
+
 /* Tracing: after ltk_trace_begin(ctx, n) every kernel launch of ltk_eval_* on this context records a CUDA
  * event before and after itself on its stream (up to n launches; n = 0 switches tracing off).
  * ltk_trace_read waits for the recorded launches and returns kind (LTK_TRACE_*), start and end in

@@ -40,6 +40,8 @@ SIGNATURES = {
     "ltk_last_error": (C.c_char_p, [_vp]),
     "ltk_set_ns": (C.c_int, [_vp, C.c_int]),
     "ltk_set_sweep_precision": (C.c_int, [_vp, C.c_int]),
+    "ltk_set_spline_mode": (C.c_int, [_vp, C.c_int]),
+    "ltk_spline_mode": (C.c_int, [_vp]),
     "ltk_trace_begin": (C.c_int, [_vp, C.c_int]),
     "ltk_trace_read": (C.c_int, [_vp, _vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_float),
                                  C.POINTER(C.c_int)]),

@@ -25,6 +25,7 @@ struct ltk_ctx {
     VehDev veh;
     VehF32 veh32;
     int sweep_bits;  // 64 (default) or 32: the optional fp32 sweep variant
+    int spline_mode; // LTK_SPLINE_TRIDIAGONAL (default) or LTK_SPLINE_FITPACK
     // scratch owned by the context
     int4* d_lut;  // engine cell table of the fused sweep (nullptr: none)
     double* d_topk_lap[2];  // ping-pong scratch of the top-k stages, grown on demand
@@ -227,10 +228,10 @@ int check_vehicle(const ltk_vehicle* v)
 
 struct WsLayout {
     long long Bp;
-    size_t kap_off, vacc_off, len_off, rot_off, mx_off, my_off, knots_off, vaccd_off, vdec_off, vmin_off, total;
+    size_t kap_off, vacc_off, len_off, rot_off, mx_off, my_off, knots_off, vaccd_off, vdec_off, vmin_off, fit_off, total;
 };
 
-WsLayout ws_layout(int ns, int N, long long B, bool dumps)
+WsLayout ws_layout(int ns, int N, long long B, bool dumps, bool fitpack = false)
 {
     WsLayout w;
     w.Bp = round_up(B < 1 ? 1 : B, 32);  // multiple of TILE and of the warp size
@@ -247,7 +248,10 @@ WsLayout ws_layout(int ns, int N, long long B, bool dumps)
     w.mx_off = off; off += (size_t)N * (size_t)w.Bp * sizeof(double);
     w.my_off = off; off += (size_t)N * (size_t)w.Bp * sizeof(double);
     w.knots_off = off; off += (size_t)(N + 1) * (size_t)w.Bp * sizeof(double);
-    w.vdec_off = w.vmin_off = w.vaccd_off = 0;
+    w.vdec_off = w.vmin_off = w.vaccd_off = w.fit_off = 0;
+    if (fitpack) {  // K1a-F scratch and hand-off (ltk_fitpack.cuh)
+        w.fit_off = off; off += fit_region_doubles(N) * (size_t)w.Bp * sizeof(double);
+    }
     if (dumps) {
         w.vaccd_off = off; off += arr;
         w.vdec_off = off; off += arr;
@@ -255,6 +259,27 @@ WsLayout ws_layout(int ns, int N, long long B, bool dumps)
     }
     w.total = off;
     return w;
+}
+
+WsLayout ctx_layout(const ltk_ctx* ctx, long long B, bool dumps)
+{
+    return ws_layout(ctx->ns, ctx->N, B, dumps, ctx->spline_mode == LTK_SPLINE_FITPACK);
+}
+
+FitArgs fit_args(const ltk_ctx* ctx, char* ws, const WsLayout& w)
+{
+    FitArgs f;
+    const size_t Bp = (size_t)w.Bp, N = (size_t)ctx->N;
+    double* p = reinterpret_cast<double*>(ws + w.fit_off);
+    f.t = p; p += (N + 7) * Bp;
+    f.rows = p; p += 7 * N * Bp;
+    f.cx = p; p += (N + 3) * Bp;
+    f.cy = p; p += (N + 3) * Bp;
+    f.w1x = p; p += (N + 2) * Bp;
+    f.w1y = p; p += (N + 2) * Bp;
+    f.w2x = p; p += (N + 1) * Bp;
+    f.w2y = p;
+    return f;
 }
 
 struct K1Config {
@@ -323,38 +348,50 @@ struct K1FConfig {
 
 bool pick_k1f(const ltk_ctx* ctx, K1FConfig* out)
 {
-    if (ctx->k1_mode == 1) return false;  // LTK_K1=old: the previous K1a + K1b pair (A/B reference)
-    if (k1a_smem_bytes(ctx->N) > ctx->smem_optin) return false;
+    const bool fitp = ctx->spline_mode == LTK_SPLINE_FITPACK;
+    if (ctx->k1_mode == 1 && !fitp) return false;  // LTK_K1=old: the previous K1a + K1b pair (A/B reference)
+    if ((fitp ? k1af_smem_bytes(ctx->N) : k1a_smem_bytes(ctx->N)) > ctx->smem_optin) return false;
     const int cand[7][2] = {{4, 256}, {4, 128}, {8, 256}, {2, 128}, {2, 64}, {1, 256}, {1, 128}};  // measured order
     for (int i = 0; i < 7; ++i) {
         int G = cand[i][0], T = cand[i][1];
         if (ctx->k1_g_override > 0 && G != ctx->k1_g_override) continue;
         if (ctx->k1_threads_override > 0 && T != ctx->k1_threads_override) continue;
-        size_t s = k1f_smem_bytes(G, T, ctx->N, ctx->ns);
+        size_t s = k1f_smem_bytes(G, T, ctx->N, ctx->ns, fitp);
         if (s <= ctx->smem_optin) { out->G = G; out->threads = T; out->smem = s; return true; }
     }
     return false;
 }
 
-template <int G, int T, int MINB>
-cudaError_t launch_k1f(const K1Args& a, size_t smem, cudaStream_t st)
+template <int G, int T, int MINB, bool FIT>
+cudaError_t launch_k1f(const K1Args& a, const FitArgs& fa, size_t smem, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(k1b_samples<G, T, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k1b_samples<G, T, MINB, FIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k1b_samples<G, T, MINB><<<(unsigned)(a.Bp / G), T, smem, st>>>(a);
+    k1b_samples<G, T, MINB, FIT><<<(unsigned)(a.Bp / G), T, smem, st>>>(a, fa);
     g_launches.fetch_add(1);
     return cudaGetLastError();
 }
 
-cudaError_t launch_k1f_cfg(const K1FConfig& c, const K1Args& a, cudaStream_t st)
+template <bool FIT>
+cudaError_t launch_k1f_cfg(const K1FConfig& c, const K1Args& a, const FitArgs& fa, cudaStream_t st)
 {
-    if (c.G == 1 && c.threads == 256) return launch_k1f<1, 256, 2>(a, c.smem, st);
-    if (c.G == 1) return launch_k1f<1, 128, 4>(a, c.smem, st);
-    if (c.G == 2 && c.threads == 128) return launch_k1f<2, 128, 8>(a, c.smem, st);
-    if (c.G == 2) return launch_k1f<2, 64, 12>(a, c.smem, st);
-    if (c.G == 4 && c.threads == 128) return launch_k1f<4, 128, 5>(a, c.smem, st);
-    if (c.G == 4) return launch_k1f<4, 256, 4>(a, c.smem, st);
-    return launch_k1f<8, 256, 2>(a, c.smem, st);
+    if (c.G == 1 && c.threads == 256) return launch_k1f<1, 256, 2, FIT>(a, fa, c.smem, st);
+    if (c.G == 1) return launch_k1f<1, 128, 4, FIT>(a, fa, c.smem, st);
+    if (c.G == 2 && c.threads == 128) return launch_k1f<2, 128, 8, FIT>(a, fa, c.smem, st);
+    if (c.G == 2) return launch_k1f<2, 64, 12, FIT>(a, fa, c.smem, st);
+    if (c.G == 4 && c.threads == 128) return launch_k1f<4, 128, 5, FIT>(a, fa, c.smem, st);
+    if (c.G == 4) return launch_k1f<4, 256, 4, FIT>(a, fa, c.smem, st);
+    return launch_k1f<8, 256, 2, FIT>(a, fa, c.smem, st);
+}
+
+cudaError_t launch_k1a_fitpack(const ltk_ctx* ctx, const K1Args& a, const FitArgs& fa, cudaStream_t st)
+{
+    size_t smem = k1af_smem_bytes(ctx->N);
+    cudaError_t e = cudaFuncSetAttribute(k1a_fitpack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k1a_fitpack<<<(unsigned)(a.Bp / 32), K1AF_THREADS, smem, st>>>(a, fa);
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_k1a_solve(const ltk_ctx* ctx, const K1Args& a, cudaStream_t st)
@@ -397,8 +434,8 @@ int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m
     K1Config cfg;
     K1FConfig fcfg;
     const bool k1_one_kernel = pick_k1f(ctx, &fcfg);
-    if (!k1_one_kernel && !pick_k1(ctx, &cfg))
-        return fail(ctx, LTK_E_UNSUPPORTED, "control-point count too large for shared memory");
+    if (!k1_one_kernel && (ctx->spline_mode == LTK_SPLINE_FITPACK || !pick_k1(ctx, &cfg)))
+        return fail(ctx, LTK_E_UNSUPPORTED, "control-point count or sampling density too large for shared memory");
     K1Args a;
     a.alphas = d_alphas; a.xy = d_xy; a.mode = d_xy ? 1 : 0; a.m = m;
     a.left = ctx->d_left; a.diff = ctx->d_diff; a.N = ctx->N; a.ns = ctx->ns;
@@ -429,12 +466,18 @@ int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m
         a.staged = 1;
         if (ctx->sweep_bits == 32 && !dumps && !k1_only)
             a.kap32 = reinterpret_cast<float*>(ws + w.vacc_off) + (size_t)(ctx->ns - 1) * (size_t)w.Bp;
+        const bool fitp = ctx->spline_mode == LTK_SPLINE_FITPACK;
+        FitArgs fa;
+        memset(&fa, 0, sizeof(fa));
+        if (fitp) fa = fit_args(ctx, ws, w);
         trace_open(LTK_TRACE_K1A, st);
-        LTK_CUDA(ctx, launch_k1a_solve(ctx, a, st));
+        if (fitp) LTK_CUDA(ctx, launch_k1a_fitpack(ctx, a, fa, st));
+        else LTK_CUDA(ctx, launch_k1a_solve(ctx, a, st));
         trace_close(st);
         if (ev) LTK_CUDA(ctx, cudaEventRecord(ev[1], st));
         trace_open(LTK_TRACE_K1B, st);
-        LTK_CUDA(ctx, launch_k1f_cfg(fcfg, a, st));
+        if (fitp) LTK_CUDA(ctx, launch_k1f_cfg<true>(fcfg, a, fa, st));
+        else LTK_CUDA(ctx, launch_k1f_cfg<false>(fcfg, a, fa, st));
         trace_close(st);
     } else {
         a.staged = cfg.staged;
@@ -619,6 +662,7 @@ int ltk_create(ltk_ctx** out, int device, const double* h_left_xy, const double*
     ctx->veh = make_vehdev(*vehicle);
     ctx->veh32 = make_vehf32(*vehicle);
     ctx->sweep_bits = 64;
+    ctx->spline_mode = LTK_SPLINE_TRIDIAGONAL;
     ctx->k1_g_override = 0;
     ctx->k1_staged_override = -1;
     if (const char* s = getenv("LTK_K1_G")) ctx->k1_g_override = atoi(s);
@@ -701,7 +745,7 @@ int ltk_set_ns(ltk_ctx* ctx, int ns)
     ctx->ns = ns;
     K1Config cfg;
     K1FConfig fcfg0;
-    if (!pick_k1f(ctx, &fcfg0) && !pick_k1(ctx, &cfg)) {
+    if (!pick_k1f(ctx, &fcfg0) && (ctx->spline_mode == LTK_SPLINE_FITPACK || !pick_k1(ctx, &cfg))) {
         ctx->ns = old;
         return fail(ctx, LTK_E_UNSUPPORTED, "no K1 configuration fits shared memory");
     }
@@ -717,6 +761,24 @@ int ltk_set_sweep_precision(ltk_ctx* ctx, int bits)
     ++ctx->epoch;
     return LTK_OK;
 }
+
+int ltk_set_spline_mode(ltk_ctx* ctx, int mode)
+{
+    if (!ctx) return LTK_E_ARG;
+    if (mode != LTK_SPLINE_TRIDIAGONAL && mode != LTK_SPLINE_FITPACK) return fail(ctx, LTK_E_ARG, "unknown spline mode");
+    if (mode == LTK_SPLINE_FITPACK && ctx->N < 5) return fail(ctx, LTK_E_UNSUPPORTED, "the FITPACK mode needs at least 5 unique control points");
+    const int old = ctx->spline_mode;
+    ctx->spline_mode = mode;
+    K1FConfig fcfg0;
+    if (mode == LTK_SPLINE_FITPACK && !pick_k1f(ctx, &fcfg0)) {
+        ctx->spline_mode = old;
+        return fail(ctx, LTK_E_UNSUPPORTED, "no FITPACK-mode K1 configuration fits shared memory");
+    }
+    ++ctx->epoch;
+    return LTK_OK;
+}
+
+int ltk_spline_mode(const ltk_ctx* ctx) { return ctx ? ctx->spline_mode : LTK_E_ARG; }
 
 int ltk_trace_begin(ltk_ctx* ctx, int max_records)
 {
@@ -766,7 +828,7 @@ int ltk_set_sweep_split(ltk_ctx* ctx, int on)
 int ltk_workspace_bytes(const ltk_ctx* ctx, int64_t B, size_t* out_bytes)
 {
     if (!ctx || !out_bytes || B < 0) return LTK_E_ARG;
-    *out_bytes = ws_layout(ctx->ns, ctx->N, B, false).total;
+    *out_bytes = ctx_layout(ctx, B, false).total;
     return LTK_OK;
 }
 
@@ -776,7 +838,7 @@ int ltk_eval_alphas(ltk_ctx* ctx, const double* d_alphas, int64_t B, double* d_l
     if (!ctx) return LTK_E_ARG;
     if (B == 0) return LTK_OK;
     if (!d_alphas || !d_lap || !d_workspace || B < 0) return fail(ctx, LTK_E_ARG, "null or negative argument");
-    WsLayout w = ws_layout(ctx->ns, ctx->N, B, false);
+    WsLayout w = ctx_layout(ctx, B, false);
     if (workspace_bytes < w.total) return fail(ctx, LTK_E_WORKSPACE, "workspace too small (see ltk_workspace_bytes)");
     DeviceGuard guard(ctx->device);
     return run_pipeline(ctx, d_alphas, nullptr, 0, B, d_lap, static_cast<char*>(d_workspace), w, false,
@@ -790,7 +852,7 @@ int ltk_eval_alphas(ltk_ctx* ctx, const double* d_alphas, int64_t B, double* d_l
 static int host_reserve(ltk_ctx* ctx, long long B)
 {
     if (!ctx->host_stream) LTK_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->host_stream, cudaStreamNonBlocking));
-    const WsLayout w = ws_layout(ctx->ns, ctx->N, B, false);
+    const WsLayout w = ctx_layout(ctx, B, false);
     if (B <= ctx->host_cap && w.total <= ctx->host_ws_bytes) return LTK_OK;
     LTK_CUDA(ctx, cudaStreamSynchronize(ctx->host_stream));
     for (int i = 0; i < LTK_HOST_GRAPHS; ++i)  // the graphs hold the old addresses
@@ -808,7 +870,7 @@ static int host_reserve(ltk_ctx* ctx, long long B)
         LTK_CUDA(ctx, cudaMalloc(&ctx->d_hout, sizeof(double) * (size_t)cap));
         ctx->host_cap = cap;
     }
-    const size_t need = ws_layout(ctx->ns, ctx->N, ctx->host_cap, false).total;
+    const size_t need = ctx_layout(ctx, ctx->host_cap, false).total;
     if (need > ctx->host_ws_bytes) {
         cudaFree(ctx->d_hws);
         ctx->d_hws = nullptr; ctx->host_ws_bytes = 0;
@@ -820,7 +882,7 @@ static int host_reserve(ltk_ctx* ctx, long long B)
 
 static int host_enqueue(ltk_ctx* ctx, long long B)
 {
-    const WsLayout w = ws_layout(ctx->ns, ctx->N, B, false);
+    const WsLayout w = ctx_layout(ctx, B, false);
     cudaStream_t st = ctx->host_stream;
     LTK_CUDA(ctx, cudaMemcpyAsync(ctx->d_hin, ctx->h_in, sizeof(double) * (size_t)B * (size_t)ctx->N, cudaMemcpyHostToDevice, st));
     int rc = run_pipeline(ctx, ctx->d_hin, nullptr, 0, B, ctx->d_hout, ctx->d_hws, w, false, st);
@@ -879,7 +941,7 @@ int ltk_eval_alphas_timed(ltk_ctx* ctx, const double* d_alphas, int64_t B, doubl
 {
     if (!ctx) return LTK_E_ARG;
     if (!d_alphas || !d_lap || !d_workspace || !h_ms || B < 1) return fail(ctx, LTK_E_ARG, "null or non-positive argument");
-    WsLayout w = ws_layout(ctx->ns, ctx->N, B, false);
+    WsLayout w = ctx_layout(ctx, B, false);
     if (workspace_bytes < w.total) return fail(ctx, LTK_E_WORKSPACE, "workspace too small (see ltk_workspace_bytes)");
     DeviceGuard guard(ctx->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -902,7 +964,7 @@ int ltk_eval_objectives(ltk_ctx* ctx, const double* d_alphas, int64_t B, double*
     if (!ctx) return LTK_E_ARG;
     if (B == 0) return LTK_OK;
     if (!d_alphas || (!d_gamma2 && !d_length) || !d_workspace || B < 0) return fail(ctx, LTK_E_ARG, "null or negative argument");
-    WsLayout w = ws_layout(ctx->ns, ctx->N, B, false);
+    WsLayout w = ctx_layout(ctx, B, false);
     if (workspace_bytes < w.total) return fail(ctx, LTK_E_WORKSPACE, "workspace too small (see ltk_workspace_bytes)");
     DeviceGuard guard(ctx->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -935,7 +997,7 @@ int ltk_eval_controls(ltk_ctx* ctx, const double* d_xy, int m, int64_t B, double
     if (B == 0) return LTK_OK;
     if (!d_xy || !d_lap || !d_workspace || B < 0) return fail(ctx, LTK_E_ARG, "null or negative argument");
     if (m != ctx->N + 1) return fail(ctx, LTK_E_ARG, "controls must have n_ctrl + 1 columns");
-    WsLayout w = ws_layout(ctx->ns, ctx->N, B, false);
+    WsLayout w = ctx_layout(ctx, B, false);
     if (workspace_bytes < w.total) return fail(ctx, LTK_E_WORKSPACE, "workspace too small (see ltk_workspace_bytes)");
     DeviceGuard guard(ctx->device);
     return run_pipeline(ctx, nullptr, d_xy, m, B, d_lap, static_cast<char*>(d_workspace), w, false,

@@ -35,12 +35,15 @@ __host__ __device__ inline int k1_chunk(int n, int cpt)
 }
 
 // doubles of scratch that alias the curvature tile (see the kernel for the carve-up)
-__host__ __device__ inline size_t k1f_scratch_doubles(int G, int N) { return (size_t)(5 * N + 1) * G; }
-
-__host__ __device__ inline size_t k1f_smem_bytes(int G, int threads, int N, int ns)
+__host__ __device__ inline size_t k1f_scratch_doubles(int G, int N, bool fitpack = false)
 {
-    size_t tile = (size_t)(ns - 1) * G, scr = k1f_scratch_doubles(G, N);
-    size_t bytes = (size_t)N * G * sizeof(Interval);                 // interval records [N][G]
+    return (size_t)(fitpack ? 5 * N + 13 : 5 * N + 1) * G;
+}
+
+__host__ __device__ inline size_t k1f_smem_bytes(int G, int threads, int N, int ns, bool fitpack = false)
+{
+    size_t tile = (size_t)(ns - 1) * G, scr = k1f_scratch_doubles(G, N, fitpack);
+    size_t bytes = (size_t)N * G * (fitpack ? sizeof(fit::FitInterval) : sizeof(Interval));  // interval records [N][G]
     bytes += (tile > scr ? tile : scr) * sizeof(double);             // curvature tile | scratch
     bytes += (size_t)(N + 1) * G * sizeof(int) + 8;                  // first sample index of each interval (+ alignment)
     bytes += (size_t)G * (sizeof(double) + sizeof(int));             // length, rotation
@@ -177,16 +180,19 @@ __global__ void __launch_bounds__(K1A_THREADS, 4) k1a_solve(K1Args a)
 // ------------------------------------------------------------------------------------------------
 // K1b
 // ------------------------------------------------------------------------------------------------
-template <int G, int T, int MINB>
-__global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a)
+// FIT = true: the records and the per-sample arithmetic of the FITPACK mode (ltk_fitpack_core.cuh); the
+// hand-off arrays are then K1a-F's knots t [N+7] and derivative coefficients wrk1 [N+2], wrk2 [N+1] per coordinate.
+template <int G, int T, int MINB, bool FIT>
+__global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a, FitArgs fa)
 {
     static_assert(32 % G == 0 && T % 32 == 0, "lanes split evenly over the candidates of a CTA");
     extern __shared__ __align__(16) unsigned char smraw[];
     const int N = a.N, n = a.ns - 1, NG = N * G;
     constexpr int NW = T / 32, CPT = T / G;
-    Interval* REC = reinterpret_cast<Interval*>(smraw);
+    using Rec = typename std::conditional<FIT, fit::FitInterval, Interval>::type;
+    Rec* REC = reinterpret_cast<Rec*>(smraw);
     double* KT = reinterpret_cast<double*>(REC + NG);
-    const size_t tile = (size_t)n * G, scr = k1f_scratch_doubles(G, N);
+    const size_t tile = (size_t)n * G, scr = k1f_scratch_doubles(G, N, FIT);
     int* IB = reinterpret_cast<int*>(KT + (tile > scr ? tile : scr));   // [N+1][G]
     double* LEN = reinterpret_cast<double*>(IB + (N + 1) * G + (((N + 1) * G) & 1));
     double* RV = LEN + G;                                               // [NW][G]
@@ -198,72 +204,122 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a)
     double* U = PY + NG;             // [N+1][G] knots
     double* RX = U + NG + G;         // [N][G] second derivatives M_x, M_y
     double* RY = RX + NG;
+    // FIT: knots t [N+7][G] (U = t + 3 rows), wrk1 x|y [N+2][G], wrk2 x|y [N+1][G]
+    double* TK = KT;
+    double* W1X = TK + (N + 7) * G;
+    double* W1Y = W1X + (N + 2) * G;
+    double* W2X = W1Y + (N + 2) * G;
+    double* W2Y = W2X + (N + 1) * G;
+    if (FIT) U = TK + 3 * G;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long b0 = (long long)blockIdx.x * G;
 
-    // ---- L: control points from the alphas; knots and second derivatives from K1a.  The hand-off loads of the
-    //      first round are issued before the control-point loads are consumed, so the two latencies overlap ----
-    double u_first = 0.0, rx_first = 0.0, ry_first = 0.0, len_first = 0.0;
-    const bool first_row = tid < NG + G, first_m = tid < NG;
-    if (first_row) u_first = a.knots[(size_t)(tid / G) * a.Bp + b0 + (tid % G)];
-    if (first_m) {
-        rx_first = a.mx[(size_t)(tid / G) * a.Bp + b0 + (tid % G)];
-        ry_first = a.my[(size_t)(tid / G) * a.Bp + b0 + (tid % G)];
-    }
-    if (tid < G) len_first = a.knots[(size_t)N * a.Bp + b0 + tid];
-    {   // T / G threads per candidate, j fastest: a candidate's alpha row is contiguous (no division by N)
-        const int g = tid / CPT;
-        long long b = b0 + g;
-        b = (b < a.B) ? b : a.B - 1;             // padding lanes repeat the last candidate
-        for (int j = tid - g * CPT; j < N; j += CPT) {
-            double x, y;
-            control_point(a, b, j, x, y);
-            PX[j * G + g] = x;
-            PY[j * G + g] = y;
+    if constexpr (FIT) {
+        // ---- L (FITPACK mode): everything comes from K1a-F, candidate-minor rows of G consecutive doubles ----
+        for (int idx = tid; idx < (N + 7) * G; idx += T) {
+            const int j = idx / G, g = idx - j * G;
+            const size_t src = (size_t)j * a.Bp + b0 + g;
+            TK[idx] = fa.t[src];
+            if (j < N + 2) { W1X[idx] = fa.w1x[src]; W1Y[idx] = fa.w1y[src]; }
+            if (j < N + 1) { W2X[idx] = fa.w2x[src]; W2Y[idx] = fa.w2y[src]; }
         }
-    }
-    if (first_row) U[tid] = u_first;
-    if (first_m) { RX[tid] = rx_first; RY[tid] = ry_first; }
-    for (int idx = tid + T; idx < NG + G; idx += T) {
-        const int j = idx / G, g = idx - j * G;
-        U[idx] = a.knots[(size_t)j * a.Bp + b0 + g];
-        if (j < N) {
-            RX[idx] = a.mx[(size_t)j * a.Bp + b0 + g];
-            RY[idx] = a.my[(size_t)j * a.Bp + b0 + g];
+        __syncthreads();
+        if (tid < G) LEN[tid] = U[NG + tid];
+        __syncthreads();
+        // ---- C (FITPACK mode): per-interval record (splder / fpbspl operands) and first sample index ---------
+        for (int idx = tid; idx < NG; idx += T) {
+            const int j = idx / G, g = idx - j * G;
+            fit::FitInterval rec;
+            rec.tm1 = TK[(j + 2) * G + g]; rec.t0 = TK[(j + 3) * G + g];
+            rec.tp1 = TK[(j + 4) * G + g]; rec.tp2 = TK[(j + 5) * G + g];
+            rec.inv01 = ddiv<false>(1.0, rec.tp1 - rec.t0);
+            rec.d1 = rec.tp1 - rec.tm1; rec.r1 = ddiv<false>(1.0, rec.d1);
+            rec.d2 = rec.tp2 - rec.t0;  rec.r2 = ddiv<false>(1.0, rec.d2);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) { rec.w1x[q] = W1X[(j + q) * G + g]; rec.w1y[q] = W1Y[(j + q) * G + g]; }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) { rec.w2x[q] = W2X[(j + q) * G + g]; rec.w2y[q] = W2Y[(j + q) * G + g]; }
+            rec.pad = 0.0;
+            REC[idx] = rec;
+            const double u0 = rec.t0;
+            const double step = LEN[g] / (double)(a.ns - 1);  // np.linspace step (tbn.py:71)
+            int i = 0;
+            if (j > 0) {
+                i = (int)ddiv<false>(u0, step);
+                i = max(0, min(i, n));
+                while (i < n && (double)i * step < u0) ++i;
+                while (i > 0 && (double)(i - 1) * step >= u0) --i;
+            }
+            IB[idx] = i;
+            if (j == N - 1) IB[NG + g] = n;
         }
-    }
-    if (tid < G) LEN[tid] = len_first;
-    __syncthreads();
-    // ---- C: per-interval coefficients  S'(t) = c1 + t (c2 + t h),  S''(t) = c2 + c3 t,  h = c3/2, and the
-    //      first sample index of every interval: IB[j] = min{ i : fl(i*step) >= U[j] } ------------------
-    for (int idx = tid; idx < NG; idx += T) {
-        const int j = idx / G, g = idx - j * G;
-        const int jn = (j + 1 == N) ? 0 : j + 1;
-        const double u0 = U[idx], u1 = U[idx + G], h = u1 - u0;  // the spline only sees the knots
-        const double mx = RX[idx], mxn = RX[jn * G + g];
-        const double my = RY[idx], myn = RY[jn * G + g];
-        const double c3x = ddiv<false>(mxn - mx, h), c3y = ddiv<false>(myn - my, h);
-        Interval rec;
-        rec.u = u0; rec.unext = u1;
-        rec.c1x = ddiv<false>(PX[jn * G + g] - PX[idx], h) - ddiv<false>(h * (2.0 * mx + mxn), 6.0);
-        rec.c1y = ddiv<false>(PY[jn * G + g] - PY[idx], h) - ddiv<false>(h * (2.0 * my + myn), 6.0);
-        rec.c2x = mx; rec.c2y = my;
-        rec.c3x = c3x; rec.c3y = c3y;
-        rec.hx = 0.5 * c3x; rec.hy = 0.5 * c3y;
-        REC[idx] = rec;
-        const double step = LEN[g] / (double)(a.ns - 1);  // np.linspace step (tbn.py:71)
-        int i = 0;
-        if (j > 0) {
-            i = (int)ddiv<false>(u0, step);
-            i = max(0, min(i, n));
-            while (i < n && (double)i * step < u0) ++i;
-            while (i > 0 && (double)(i - 1) * step >= u0) --i;
+        __syncthreads();
+    } else {
+
+        // ---- L: control points from the alphas; knots and second derivatives from K1a.  The hand-off loads of the
+        //      first round are issued before the control-point loads are consumed, so the two latencies overlap ----
+        double u_first = 0.0, rx_first = 0.0, ry_first = 0.0, len_first = 0.0;
+        const bool first_row = tid < NG + G, first_m = tid < NG;
+        if (first_row) u_first = a.knots[(size_t)(tid / G) * a.Bp + b0 + (tid % G)];
+        if (first_m) {
+            rx_first = a.mx[(size_t)(tid / G) * a.Bp + b0 + (tid % G)];
+            ry_first = a.my[(size_t)(tid / G) * a.Bp + b0 + (tid % G)];
         }
-        IB[idx] = i;
-        if (j == N - 1) IB[NG + g] = n;
+        if (tid < G) len_first = a.knots[(size_t)N * a.Bp + b0 + tid];
+        {   // T / G threads per candidate, j fastest: a candidate's alpha row is contiguous (no division by N)
+            const int g = tid / CPT;
+            long long b = b0 + g;
+            b = (b < a.B) ? b : a.B - 1;             // padding lanes repeat the last candidate
+            for (int j = tid - g * CPT; j < N; j += CPT) {
+                double x, y;
+                control_point(a, b, j, x, y);
+                PX[j * G + g] = x;
+                PY[j * G + g] = y;
+            }
+        }
+        if (first_row) U[tid] = u_first;
+        if (first_m) { RX[tid] = rx_first; RY[tid] = ry_first; }
+        for (int idx = tid + T; idx < NG + G; idx += T) {
+            const int j = idx / G, g = idx - j * G;
+            U[idx] = a.knots[(size_t)j * a.Bp + b0 + g];
+            if (j < N) {
+                RX[idx] = a.mx[(size_t)j * a.Bp + b0 + g];
+                RY[idx] = a.my[(size_t)j * a.Bp + b0 + g];
+            }
+        }
+        if (tid < G) LEN[tid] = len_first;
+        __syncthreads();
+        // ---- C: per-interval coefficients  S'(t) = c1 + t (c2 + t h),  S''(t) = c2 + c3 t,  h = c3/2, and the
+        //      first sample index of every interval: IB[j] = min{ i : fl(i*step) >= U[j] } ------------------
+        for (int idx = tid; idx < NG; idx += T) {
+            const int j = idx / G, g = idx - j * G;
+            const int jn = (j + 1 == N) ? 0 : j + 1;
+            const double u0 = U[idx], u1 = U[idx + G], h = u1 - u0;  // the spline only sees the knots
+            const double mx = RX[idx], mxn = RX[jn * G + g];
+            const double my = RY[idx], myn = RY[jn * G + g];
+            const double c3x = ddiv<false>(mxn - mx, h), c3y = ddiv<false>(myn - my, h);
+            Interval rec;
+            rec.u = u0; rec.unext = u1;
+            rec.c1x = ddiv<false>(PX[jn * G + g] - PX[idx], h) - ddiv<false>(h * (2.0 * mx + mxn), 6.0);
+            rec.c1y = ddiv<false>(PY[jn * G + g] - PY[idx], h) - ddiv<false>(h * (2.0 * my + myn), 6.0);
+            rec.c2x = mx; rec.c2y = my;
+            rec.c3x = c3x; rec.c3y = c3y;
+            rec.hx = 0.5 * c3x; rec.hy = 0.5 * c3y;
+            REC[idx] = rec;
+            const double step = LEN[g] / (double)(a.ns - 1);  // np.linspace step (tbn.py:71)
+            int i = 0;
+            if (j > 0) {
+                i = (int)ddiv<false>(u0, step);
+                i = max(0, min(i, n));
+                while (i < n && (double)i * step < u0) ++i;
+                while (i > 0 && (double)(i - 1) * step >= u0) --i;
+            }
+            IB[idx] = i;
+            if (j == N - 1) IB[NG + g] = n;
+        }
+        __syncthreads();  // scratch is dead from here on: the tile region now takes curvatures
     }
-    __syncthreads();  // scratch is dead from here on: the tile region now takes curvatures
 
     // ---- K: curvature at the samples ----------------------------------------------------------------------
     const int g = tid % G, c = tid / G;
@@ -283,7 +339,7 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a)
         // per-interval loops diverge -- interval boundaries differ from lane to lane -- and ran at 19 of
         // 32 lanes); the interval switch is an integer test that fires about once per 20 samples.
         int j = lo;
-        Interval v = REC[j * G + g];
+        Rec v = REC[j * G + g];
         int inext = IB[(j + 1) * G + g];
         for (int i = i0; i < i1; ++i) {
             while (i >= inext) {
@@ -291,15 +347,21 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a)
                 v = REC[j * G + g];
                 inext = IB[(j + 1) * G + g];
             }
-            // |x'y'' - y'x''| / (x'^2 + y'^2)^(3/2)   (path.py:58,61), Horner form, explicit FMAs
             const double s = (double)i * step;
-            const double t = s - v.u;
-            const double ddx = fma(v.c3x, t, v.c2x), ddy = fma(v.c3y, t, v.c2y);
-            const double dx = fma(t, fma(v.hx, t, v.c2x), v.c1x);
-            const double dy = fma(t, fma(v.hy, t, v.c2y), v.c1y);
-            const double cross = fabs(fma(dx, ddy, -(dy * ddx)));
-            const double n2 = fma(dx, dx, dy * dy);
-            const double k = ddiv<false>(cross, n2 * dsqrt<false>(n2));
+            double k;
+            if constexpr (FIT) {
+                double dx, dy, ddx, ddy;
+                k = fit::curvature_at(v, s, dx, dy, ddx, ddy);
+            } else {
+                // |x'y'' - y'x''| / (x'^2 + y'^2)^(3/2)   (path.py:58,61), Horner form, explicit FMAs
+                const double t = s - v.u;
+                const double ddx = fma(v.c3x, t, v.c2x), ddy = fma(v.c3y, t, v.c2y);
+                const double dx = fma(t, fma(v.hx, t, v.c2x), v.c1x);
+                const double dy = fma(t, fma(v.hy, t, v.c2y), v.c1y);
+                const double cross = fabs(fma(dx, ddy, -(dy * ddx)));
+                const double n2 = fma(dx, dx, dy * dy);
+                k = ddiv<false>(cross, n2 * dsqrt<false>(n2));
+            }
             KT[(size_t)i * G + g] = k;
             if (k > best) { best = k; bi = i; }
         }

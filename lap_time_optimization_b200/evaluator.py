@@ -23,7 +23,10 @@ class Lane:
 
 
 class LapTimeEvaluator:
-    def __init__(self, track, vehicle, mode="bayes", ns=None, device=None, max_workspace_bytes=None):
+    SPLINE_MODES = {"tridiagonal": 0, "fitpack": 1}  # LTK_SPLINE_* (include/ltk.h)
+
+    def __init__(self, track, vehicle, mode="bayes", ns=None, device=None, max_workspace_bytes=None,
+                 spline="tridiagonal"):
         torch = _device.torch_cuda()
         self.torch = torch
         self.lib = _native.load()
@@ -46,6 +49,20 @@ class LapTimeEvaluator:
             free, _total = torch.cuda.mem_get_info(self.device)
             max_workspace_bytes = int(free * 0.8)
         self.max_workspace_bytes = max_workspace_bytes
+        self.spline = "tridiagonal"
+        self._split_on = True
+        if spline != "tridiagonal":
+            self.set_spline_mode(spline)
+
+    def set_spline_mode(self, spline):
+        """"tridiagonal" (default, fastest): classical cyclic-tridiagonal periodic spline.  "fitpack": SciPy
+        FITPACK's own arithmetic (fpclos Givens QR, splder) -- the bits `splprep(per=1)` / `splev` give the
+        reference (path.py:25, :51-54); lap times then match the reference bit for bit on most candidates."""
+        _native.check(self.lib.ltk_set_spline_mode(self._ctx, self.SPLINE_MODES[spline]), self._ctx)
+        self.spline = spline
+        self._ws = None  # the workspace layout depends on the mode
+        for lane in (getattr(self, "_lanes", None) or [])[1:]:
+            lane.ev.set_spline_mode(spline)
 
     # -- lifetime ---------------------------------------------------------------------------------
     def close(self):
@@ -114,15 +131,23 @@ class LapTimeEvaluator:
             self.max_workspace_bytes = min(self.max_workspace_bytes, int(torch.cuda.mem_get_info(self.device)[0] * 0.8) // n)
         while len(cur) < n:
             ev = self if not cur else LapTimeEvaluator(self.track, self.vehicle, self.mode, self.ns, self.device.index,
-                                                       self.max_workspace_bytes)
-            if cur and getattr(self, "sweep_bits", 64) != 64:
-                ev.set_sweep_precision(self.sweep_bits)
+                                                       self.max_workspace_bytes, spline=self.spline)
+            if cur:
+                ev.wave_lanes = 1  # a lane scores its population itself; only the owner fans out
+                if getattr(self, "sweep_bits", 64) != 64:
+                    ev.set_sweep_precision(self.sweep_bits)
             cur.append(Lane(ev, torch.cuda.Stream(self.device)))
         self._lanes = cur
-        if n > 1:  # several populations in flight: one sweep launch each (see ltk_set_sweep_split)
-            for lane in cur:
-                _native.check(self.lib.ltk_set_sweep_split(lane.ev._ctx, 0), lane.ev._ctx)
+        # several populations in flight: one sweep launch each (see ltk_set_sweep_split); a later
+        # single-population call on this evaluator switches the split back on (lap_times_device)
+        for lane in cur[:n]:
+            lane.ev._set_split(n <= 1)
         return cur[:n]
+
+    def _set_split(self, on):
+        if self._split_on != bool(on):
+            _native.check(self.lib.ltk_set_sweep_split(self._ctx, int(bool(on))), self._ctx)
+            self._split_on = bool(on)
 
     # -- sizing -----------------------------------------------------------------------------------
     def workspace_bytes(self, B):
@@ -141,12 +166,15 @@ class LapTimeEvaluator:
         if self._ws is None or self._ws.numel() < need:
             self._ws = None
             self._ws = self.torch.empty(need, dtype=self.torch.uint8, device=self.device)
+        # lanes run on streams other than the one the block was allocated on
+        self._ws.record_stream(self.torch.cuda.current_stream(self.device))
         return self._ws
 
     # -- evaluation -------------------------------------------------------------------------------
-    def lap_times_device(self, alphas, out=None):
+    def lap_times_device(self, alphas, out=None, _lane=False):
         """alphas: float64 CUDA tensor [B, n_alpha] (contiguous) -> float64 CUDA tensor [B].
-        Asynchronous on the current stream."""
+        Asynchronous on the current stream.  (`_lane`: set by the multi-lane drivers, which manage the
+        sweep split themselves.)"""
         torch = self.torch
         if alphas.dtype != torch.float64 or not alphas.is_cuda:
             raise ValueError("alphas must be a float64 CUDA tensor")
@@ -158,6 +186,8 @@ class LapTimeEvaluator:
             out = torch.empty(B, dtype=torch.float64, device=self.device)
         if B >= 2 * self.WAVE and self.wave_lanes > 1:
             return self._lap_times_waves(alphas, out)
+        if not _lane:
+            self._set_split(True)
         chunk = self.max_batch()
         st = _device.stream_ptr(torch, self.device)
         for lo in range(0, B, chunk):
@@ -351,6 +381,12 @@ class LapTimeEvaluator:
         if getattr(self, "_copy_streams", None) is None:
             self._copy_streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
         copy_in, copy_out = self._copy_streams
+        # join the caller's stream: lane 0 is this evaluator (its workspace, top-k scratch and ticket), and
+        # earlier asynchronous calls on the current stream may still be using them
+        entry = torch.cuda.Event()
+        entry.record(torch.cuda.current_stream(dev))
+        for st_ in [lane.stream for lane in pool] + [copy_in, copy_out]:
+            st_.wait_event(entry)
         nslot = max(len(pool), int(slots) if slots else 2 * len(pool))
         slots = [None] * nslot
         pending = []  # (slot index, B) in submission order
@@ -401,7 +437,7 @@ class LapTimeEvaluator:
                 lane.stream.wait_event(sl["ev_in"])
                 if sl["used"]:
                     lane.stream.wait_event(sl["ev_out"])  # d_lap of this slot has been read back
-                d_lap = lane.ev.lap_times_device(sl["d_in"][:B], out=sl["d_lap"][:B])
+                d_lap = lane.ev.lap_times_device(sl["d_in"][:B], out=sl["d_lap"][:B], _lane=len(pool) > 1)
                 best, idx = lane.ev.topk_device(d_lap, k, index_base=base)
                 sl["ev_done"].record(lane.stream)
             if finish is not None:
@@ -435,7 +471,7 @@ class LapTimeEvaluator:
         for i, pop in enumerate(populations):
             lane = pool[i % len(pool)]
             with torch.cuda.stream(lane.stream):
-                d_lap = lane.ev.lap_times_device(pop, out=outs[i % len(pool)])
+                d_lap = lane.ev.lap_times_device(pop, out=outs[i % len(pool)], _lane=len(pool) > 1)
                 last = lane.ev.topk_device(d_lap, k, index_base=index_base)
                 if finish is not None:
                     done = torch.cuda.Event()

@@ -2,8 +2,11 @@
   (a) the golden vectors of the unmodified reference,
   (b) the level-2 C oracle on identical inputs -- bit for bit, at BASELINE.json's full size,
   (c) size-independent properties (idempotence, permutation / chunking invariance, ragged batches).
-Tolerances (fp64): CUDA == C oracle exactly; lap vs reference <= 1e-9 relative on the BASELINE
-populations except the documented friction-circle noise floor (DESIGN.md "Parity")."""
+Tolerances (fp64): CUDA == C oracle exactly, in both spline modes.  Against the reference:
+  FITPACK mode (LTK_SPLINE_FITPACK): lap <= 1e-9 relative on EVERY candidate (observed <= 7e-10 against an
+      AVX512 host's numpy, <= 5e-11 against numpy's baseline dispatch, median at the ulp level);
+  default mode (cyclic tridiagonal spline): median <= 1e-10, p99 <= 1e-9, with the documented friction-circle
+      tail (about one candidate in 4,000 above 1e-9, DESIGN.md "Parity")."""
 import os
 
 import numpy as np
@@ -19,12 +22,20 @@ pytestmark = pytest.mark.gpu
 PROFILE_KEYS = ("k", "v_local", "v_acclim", "v_declim", "v")
 
 
-def make(name, ns=None):
+def make(name, ns=None, spline="tridiagonal"):
     tj, width, vj, mode = case_setup(name)
     track = ltk.Track(tj, track_width=width, quiet=True)
-    ev = ltk.LapTimeEvaluator(track, ltk.load_vehicle(vj), mode, ns)
-    co = c_oracle.COracle(OracleTrack(tj, width), load_vehicle(vj), mode, ns, device_sum_order=True)
+    ev = ltk.LapTimeEvaluator(track, ltk.load_vehicle(vj), mode, ns, spline=spline)
+    co = c_oracle.COracle(OracleTrack(tj, width), load_vehicle(vj), mode, ns, device_sum_order=True, spline=spline)
     return ev, co
+
+
+def port_laps(name, alphas, ns=None):
+    """The reference-equivalent Python port (same SciPy / numpy calls as the reference) on all host cores."""
+    from oracle.reference_port import lap_times_pool
+
+    tj, width, vj, mode = case_setup(name)
+    return lap_times_pool(tj, width, vj, alphas, mode=mode, ns=ns)
 
 
 @pytest.fixture(scope="module")
@@ -148,19 +159,95 @@ def test_every_track_vehicle_and_mode_bit_exact(track, veh, mode):
     ev.close()
 
 
-def test_reference_port_sample_within_tolerance(buckmore):
-    """End to end against the reference-equivalent Python port on fresh random candidates."""
-    from oracle.reference_port import OracleEvaluator
-
+def test_reference_port_sample_default_mode(buckmore):
+    """Default (tridiagonal) spline, end to end against the reference-equivalent port on 4,096 rows of BASELINE
+    config 2's population.  The distribution is asserted as measured (DESIGN.md "Parity"): median 2.5e-11,
+    p99 1.6e-10, about one candidate in 4,000 above 1e-9 (TBR18's friction-circle cancellation amplifying the
+    ~1e-13 curvature difference between two spline solvers), worst case seen 3.7e-9."""
     ev, _ = buckmore
-    tj, width, vj, mode = case_setup("buckmore_tbr18_bayes")
-    port = OracleEvaluator(OracleTrack(tj, width), load_vehicle(vj), mode)
-    a = np.random.default_rng(77).uniform(0.0, 0.99, (96, ev.n_alpha))
-    rel = rel_err(ev.lap_times(a), [port.lap_time(x) for x in a])
-    # 1e-9 is the north-star tolerance; the reference's own friction-circle noise floor (a 1-ulp change
-    # of one curvature sample moves its lap time by up to ~4e-9, DESIGN.md "Parity") is allowed to push
-    # isolated candidates past it -- bounded here at 2 % of the sample and 2e-8 absolute worst case.
-    assert np.median(rel) <= 1e-10 and np.mean(rel <= 1e-9) >= 0.98 and rel.max() <= 2e-8
+    a = np.random.default_rng(1002).uniform(0.0, 0.99, (65536, ev.n_alpha))[:4096]
+    rel = rel_err(ev.lap_times(a), port_laps("buckmore_tbr18_bayes", a))
+    assert np.median(rel) <= 5e-11 and np.quantile(rel, 0.99) <= 4e-10
+    assert int((rel > 1e-9).sum()) <= 6 and rel.max() <= 1e-8
+
+
+# ---- FITPACK mode: the reference's own spline arithmetic ---------------------------------------------------
+@pytest.mark.parametrize("name", golden_cases())
+def test_fitpack_mode_golden_case(name, golden):
+    g = golden(name)
+    ev, co = make(name, int(g["ns"]), spline="fitpack")
+    laps = ev.lap_times(g["alphas"])
+    assert np.array_equal(laps, co.lap_times(g["alphas"])), "CUDA differs from the C oracle"
+    # every candidate inside the north-star tolerance, against the reference as run on an AVX512 host (numpy's
+    # SVML pow) and on numpy's baseline dispatch (libm pow); the remaining difference to the latter is the lap
+    # sum's order (1-2 ulp) and x*x against libm pow(x, 2) (1 ulp in 0.08 % of the squares)
+    assert rel_err(laps, g["laps"]).max() <= 1e-9
+    rb = rel_err(laps, g["laps_base"])
+    assert rb.max() <= 1e-10 and np.median(rb) <= 2e-15
+    for i in range(int(g["n_profiles"])):
+        pr, cp = ev.profile(g["alphas"][i]), co.profile(g["alphas"][i])
+        for key in PROFILE_KEYS:
+            assert np.array_equal(pr[key], cp[key]), key
+        assert pr["lap"] == laps[i] and pr["length"] == g["prof_length"][i]
+        assert np.array_equal(pr["s"], g["prof_s"][i])
+        kb = g["prof_k_base"][i]
+        assert (pr["k"] != kb).mean() <= 0.005  # libm pow is not always correctly rounded
+        assert np.all(np.abs(pr["k"] - kb) <= 2 * np.spacing(np.maximum(pr["k"], kb)))
+    ev.close()
+
+
+@pytest.mark.parametrize("veh", ["tbr18", "mx5"])
+def test_fitpack_mode_full_size_population(veh):
+    """BASELINE config 2 (65,536 candidates) in FITPACK mode: bit-equal to the C oracle, top-10 identical, and a
+    4,096-row sample against the reference-equivalent port with EVERY row inside 1e-9."""
+    name = f"buckmore_{veh}_bayes"
+    ev, co = make(name, spline="fitpack")
+    a = np.random.default_rng(1002).uniform(0.0, 0.99, (65536, ev.n_alpha))
+    d_lap = ev.lap_times_device(torch.as_tensor(a).cuda())
+    laps, ref = d_lap.cpu().numpy(), co.lap_times(a)
+    assert np.array_equal(laps, ref)
+    best, idx = ev.topk(d_lap, 10)
+    o_idx, o_best = top_k(list(ref), 10)
+    assert np.array_equal(idx, o_idx) and np.array_equal(best, o_best)
+    rows = np.random.default_rng(4).choice(len(a), 4096, replace=False)
+    port = port_laps(name, a[rows])
+    rel = rel_err(laps[rows], port)
+    assert int((rel > 1e-9).sum()) == 0, (rel.max(), int((rel > 1e-9).sum()))
+    assert np.median(rel) <= 1e-14 and np.quantile(rel, 0.99) <= 2e-10
+    p_idx, _ = top_k(list(port), 10)
+    s_idx, _ = top_k(list(laps[rows]), 10)
+    assert np.array_equal(p_idx, s_idx)
+    ev.close()
+
+
+@pytest.mark.parametrize("track,mode", [("clay", "bayes"), ("gyg", "full"), ("whilton", "full"), ("whilton", "bayes")])
+def test_fitpack_mode_other_tracks(track, mode):
+    ev, co = make(f"{track}_tbr18_{mode}", spline="fitpack")
+    a = np.random.default_rng(len(track) + len(mode)).uniform(0.0, 0.99, (2048, ev.n_alpha))
+    a[0] = 0.5
+    a[1] = np.random.default_rng(1).uniform(-0.46, 1.97, ev.n_alpha)  # COBYLA leaves the box
+    assert np.array_equal(ev.lap_times(a), co.lap_times(a))
+    ev.close()
+
+
+def test_spline_mode_switch_and_ragged(buckmore):
+    """Switching modes on a live evaluator (workspace layout changes) and ragged batch sizes in FITPACK mode."""
+    ev, co = buckmore
+    _, cof = make_oracle_only("buckmore_tbr18_bayes", "fitpack")
+    a = np.random.default_rng(9).uniform(0.0, 0.99, (1000, ev.n_alpha))
+    try:
+        ev.set_spline_mode("fitpack")
+        for B in (1, 31, 33, 1000):
+            assert np.array_equal(ev.lap_times(a[:B]), cof.lap_times(a[:B]))
+    finally:
+        ev.set_spline_mode("tridiagonal")
+    assert np.array_equal(ev.lap_times(a), co.lap_times(a))
+
+
+def make_oracle_only(name, spline):
+    tj, width, vj, mode = case_setup(name)
+    return None, c_oracle.COracle(OracleTrack(tj, width), load_vehicle(vj), mode, None, device_sum_order=True,
+                                  spline=spline)
 
 
 # ---- properties ----------------------------------------------------------------------------------------

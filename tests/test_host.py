@@ -179,3 +179,77 @@ def test_result_artefact_writers(tmp_path):
     assert left["path"]["x"] == track.old_left[0].tolist() and len(left["path"]["y"]) == track.old_left.shape[1]
     assert json.load(open(d / "widths.json"))["width"] == track.widths.tolist()
     assert json.load(open(d / "velocities.json")) == {"name": "velocities", "velocities": [0.0, 1.0, 2.0, 3.0, 4.0, 5.0]}
+
+
+# ---- the FITPACK-mode device arithmetic, compiled for the host ------------------------------------------
+@pytest.fixture(scope="module")
+def fitcore(tmp_path_factory):
+    """g++ build of lap_time_optimization_b200/csrc/ltk_fitpack_core.cuh (the __host__ __device__ code the
+    CUDA kernels k1a_fitpack / k1b_samples<FIT> run), -ffp-contract=off like nvcc -fmad=false."""
+    import subprocess
+
+    so = str(tmp_path_factory.mktemp("fitcore") / "libfitcore.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-o", so,
+                           os.path.join(ROOT, "tests", "native", "fitcore_host.cpp"), "-lm"])
+    lib = ctypes.CDLL(so)
+    dp = ctypes.POINTER(ctypes.c_double)
+    lib.fitcore_solve.argtypes = [ctypes.c_int] + [dp] * 10
+    lib.fitcore_curvature.argtypes = [ctypes.c_int] + [dp] * 6 + [ctypes.c_int] + [dp] * 5
+    return lib
+
+
+def _fitcore_run(lib, pts, u, x):
+    dp = ctypes.POINTER(ctypes.c_double)
+    p = lambda a: a.ctypes.data_as(dp)  # noqa: E731
+    N = pts.shape[1] - 1
+    px, py = np.ascontiguousarray(pts[0, :N]), np.ascontiguousarray(pts[1, :N])
+    out = {k: np.zeros(n) for k, n in (("t", N + 7), ("cx", N + 3), ("cy", N + 3), ("w1x", N + 2), ("w1y", N + 2),
+                                       ("w2x", N + 1), ("w2y", N + 1))}
+    u = np.ascontiguousarray(u)
+    assert lib.fitcore_solve(N, p(px), p(py), p(u), *[p(out[k]) for k in ("t", "cx", "cy", "w1x", "w1y", "w2x", "w2y")]) == 0
+    x = np.ascontiguousarray(x)
+    ev = {k: np.zeros(x.size) for k in ("k", "dx", "dy", "ddx", "ddy")}
+    lib.fitcore_curvature(N, *[p(out[k]) for k in ("t", "w1x", "w1y", "w2x", "w2y")], p(x), x.size,
+                          *[p(ev[k]) for k in ("k", "dx", "dy", "ddx", "ddy")])
+    out.update(ev)
+    return out
+
+
+def test_device_fitpack_arithmetic_equals_scipy(fitcore):
+    """The single-pass register-window Givens QR of the kernels == splprep(k=3, s=0, per=1) bit for bit, and its
+    derivative evaluation == splev(der=1|2), on random closed polygons of 5 .. 170 points."""
+    from scipy.interpolate import splev, splprep
+
+    rng = np.random.default_rng(21)
+    for trial in range(80):
+        m = int(rng.integers(6, 172))
+        th = np.sort(rng.uniform(0, 2 * np.pi, m - 1))
+        r = rng.uniform(50, 120, m - 1)
+        pts = np.array([r * np.cos(th), r * np.sin(th)])
+        pts = np.concatenate([pts, pts[:, :1]], axis=1)
+        u = np.append(0, np.cumsum(np.linalg.norm(np.diff(pts, axis=1), axis=0)))
+        (t, c, k), _ = splprep(pts.copy(), u=u, k=3, s=0, per=1)
+        x = np.linspace(0, u[-1], 500)[:-1]
+        got = _fitcore_run(fitcore, pts, u, x)
+        assert np.array_equal(got["t"], t) and np.array_equal(got["cx"], c[0]) and np.array_equal(got["cy"], c[1])
+        d1, d2 = splev(x, (t, c, k), der=1), splev(x, (t, c, k), der=2)
+        for key, want in (("dx", d1[0]), ("dy", d1[1]), ("ddx", d2[0]), ("ddy", d2[1])):
+            assert np.array_equal(got[key], want), (trial, key)
+
+
+@pytest.mark.parametrize("name", ["buckmore_tbr18_bayes", "buckmore_tbr18_full", "whilton_mx5_full", "gyg_tbr18_bayes"])
+def test_device_fitpack_arithmetic_equals_reference_and_oracle(fitcore, name):
+    """Same code against the spline the unmodified reference built (golden tck, derivatives) and against the C
+    oracle's curvature (oracle/lap_oracle.c in FITPACK mode), bit for bit."""
+    from conftest import case_setup
+
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", name + ".npz")))
+    tj, width, vj, mode = case_setup(name)
+    co = c_oracle.COracle(OracleTrack(tj, width), load_vehicle(vj), mode, int(g["ns"]), spline="fitpack")
+    for i in range(int(g["n_profiles"])):
+        got = _fitcore_run(fitcore, g["prof_controls"][i], g["prof_dists"][i], g["prof_s"][i][:-1])
+        assert np.array_equal(got["t"], g["prof_tck_t"][i])
+        assert np.array_equal(got["cx"], g["prof_tck_cx"][i]) and np.array_equal(got["cy"], g["prof_tck_cy"][i])
+        for key in ("dx", "dy", "ddx", "ddy"):
+            assert np.array_equal(got[key], g["prof_" + key][i]), key
+        assert np.array_equal(got["k"], co.profile(g["alphas"][i])["k"])
