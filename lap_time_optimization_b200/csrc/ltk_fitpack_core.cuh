@@ -71,6 +71,66 @@ LTK_HD void givens(double piv, double& ww, double& c, double& s)
     ww = dd;
 }
 
+// Two independent divisions / square roots written stage by stage: a warp issues in order, so two dependency
+// chains only overlap as far as the instruction stream alternates between them (same trick as dsqrt_pair in
+// ltk_sweep_fused.cuh).  Same operations, same results as two scalar calls.
+LTK_HD void fdiv2(double a0, double b0, double a1, double b1, double& q0, double& q1)
+{
+#if defined(__CUDA_ARCH__)
+    double y0 = rcp_seed(b0), y1 = rcp_seed(b1);
+    double e0 = fma(y0, -b0, 1.0), e1 = fma(y1, -b1, 1.0);
+    e0 = fma(e0, e0, e0); e1 = fma(e1, e1, e1);
+    y0 = fma(y0, e0, y0); y1 = fma(y1, e1, y1);
+    e0 = fma(y0, -b0, 1.0); e1 = fma(y1, -b1, 1.0);
+    y0 = fma(y0, e0, y0); y1 = fma(y1, e1, y1);
+    const double p0 = y0 * a0, p1 = y1 * a1;
+    const double r0 = fma(p0, -b0, a0), r1 = fma(p1, -b1, a1);
+    q0 = fma(y0, r0, p0); q1 = fma(y1, r1, p1);
+#else
+    q0 = a0 / b0; q1 = a1 / b1;
+#endif
+}
+// c = w / d and s = p / d for two rotations: one refined reciprocal per divisor, four quotients
+LTK_HD void fdiv2x2(double w0, double p0, double d0, double w1, double p1, double d1, double& c0, double& s0,
+                    double& c1, double& s1)
+{
+#if defined(__CUDA_ARCH__)
+    double y0 = rcp_seed(d0), y1 = rcp_seed(d1);
+    double e0 = fma(y0, -d0, 1.0), e1 = fma(y1, -d1, 1.0);
+    e0 = fma(e0, e0, e0); e1 = fma(e1, e1, e1);
+    y0 = fma(y0, e0, y0); y1 = fma(y1, e1, y1);
+    e0 = fma(y0, -d0, 1.0); e1 = fma(y1, -d1, 1.0);
+    y0 = fma(y0, e0, y0); y1 = fma(y1, e1, y1);
+    const double qc0 = y0 * w0, qc1 = y1 * w1, qs0 = y0 * p0, qs1 = y1 * p1;
+    const double rc0 = fma(qc0, -d0, w0), rc1 = fma(qc1, -d1, w1), rs0 = fma(qs0, -d0, p0), rs1 = fma(qs1, -d1, p1);
+    c0 = fma(y0, rc0, qc0); c1 = fma(y1, rc1, qc1); s0 = fma(y0, rs0, qs0); s1 = fma(y1, rs1, qs1);
+#else
+    c0 = w0 / d0; s0 = p0 / d0; c1 = w1 / d1; s1 = p1 / d1;
+#endif
+}
+LTK_HD void fsqrt2(double x0, double x1, double& r0, double& r1)
+{
+#if defined(__CUDA_ARCH__)
+    dsqrt_pair(x0, x1, r0, r1);
+#else
+    r0 = sqrt(x0); r1 = sqrt(x1);
+#endif
+}
+
+// Two independent fpgivs set-ups (both pivots non-zero), branch-free and interleaved.
+LTK_HD void givens2(double p0, double& w0, double& c0, double& s0, double p1, double& w1, double& c1, double& s1)
+{
+    const double a0 = fabs(p0), a1 = fabs(p1);
+    const bool g0 = a0 >= w0, g1 = a1 >= w1;
+    double r0, r1;
+    fdiv2(g0 ? w0 : p0, g0 ? p0 : w0, g1 ? w1 : p1, g1 ? p1 : w1, r0, r1);
+    double t0, t1;
+    fsqrt2(1.0 + r0 * r0, 1.0 + r1 * r1, t0, t1);
+    const double d0 = (g0 ? a0 : w0) * t0, d1 = (g1 ? a1 : w1) * t1;
+    fdiv2x2(w0, p0, d0, w1, p1, d1, c0, s0, c1, s1);
+    w0 = d0; w1 = d1;
+}
+
 // fprota
 LTK_HD void rota(double c, double s, double& a, double& b)
 {
@@ -89,12 +149,12 @@ LTK_HD void bspl_at_knot(double tm2, double tm1, double t0, double tp1, double t
     f = fdiv(g1, tp1 - tm1);
     g1 = f * a;                                          // degree 2: (g1, g2, 0)
     double g2 = f * (t0 - tm1);
-    f = fdiv(g1, tp1 - tm2);
-    h1 = f * a;                                          // degree 3
-    h2 = f * (t0 - tm2);
-    f = fdiv(g2, tp2 - tm1);
-    h2 = h2 + f * (tp2 - t0);
-    h3 = f * (t0 - tm1);
+    double fa, fb;
+    fdiv2(g1, tp1 - tm2, g2, tp2 - tm1, fa, fb);
+    h1 = fa * a;                                         // degree 3
+    h2 = fa * (t0 - tm2);
+    h2 = h2 + fb * (tp2 - t0);
+    h3 = fb * (t0 - tm1);
 }
 
 struct Row {  // one row of the triangular factor: band part a1(j, 1..3), periodic part a2(j, 1..2), z(j) per dim
@@ -105,16 +165,9 @@ struct WrapRow {  // a wrapping data row being rotated through the factor
     double h1[3], h2[2], x, y;
 };
 
-// one step of "rotation with the rows 1,2,...n10 of matrix a" (fpclos) for row j (1-based), n10 = N - 2
-LTK_HD void wrap_rotate(WrapRow& S, Row& R, int j, int n10)
+// the part of "rotation with the rows 1,2,...n10 of matrix a" (fpclos) that follows fpgivs, row j (1-based)
+LTK_HD void wrap_apply(WrapRow& S, Row& R, int j, int n10, double c, double s)
 {
-    const double piv = S.h1[0];
-    if (piv == 0.0) {
-        S.h1[0] = S.h1[1]; S.h1[1] = S.h1[2]; S.h1[2] = 0.0;
-        return;
-    }
-    double c, s;
-    givens(piv, R.a, c, s);
     rota(c, s, S.x, R.zx);
     rota(c, s, S.y, R.zy);
     rota(c, s, S.h2[0], R.e1);
@@ -129,6 +182,17 @@ LTK_HD void wrap_rotate(WrapRow& S, Row& R, int j, int n10)
     } else {
         S.h1[1] = 0.0;
     }
+}
+LTK_HD void wrap_rotate(WrapRow& S, Row& R, int j, int n10)
+{
+    const double piv = S.h1[0];
+    if (piv == 0.0) {
+        S.h1[0] = S.h1[1]; S.h1[1] = S.h1[2]; S.h1[2] = 0.0;
+        return;
+    }
+    double c, s;
+    givens(piv, R.a, c, s);
+    wrap_apply(S, R, j, n10, c, s);
 }
 
 // "rotation with the rows n10+1,...n7": R0 = row n10+1 (a2 entries in a, b), R1 = row n10+2 (a2 entry in a)
@@ -152,18 +216,30 @@ LTK_HD void wrap_tail(WrapRow& S, Row& R0, Row& R1)
 
 // Addressing of one candidate's arrays.
 struct Io {
-    const double* px; const double* py; long sp;  // unique control points [N]
     double* t; long st;                            // knots [N + 7]; entries 3 .. N+3 hold the chord-length knots on entry
     double* rows; long sr;                         // scratch: 7 N entries
-    double* cx; double* cy; long sc;               // B-spline coefficients [N + 3] each (nullptr: not wanted)
+    double* cx; double* cy; long sc;               // B-spline coefficients [N + 3] each
     double* w1x; double* w1y; double* w2x; double* w2y; long sw;  // derivative coefficients [N+2], [N+2], [N+1], [N+1]
 };
 
 #define LTK_T(l) io.t[(long)((l) - 1) * io.st]          /* 1-based knot index as in FITPACK */
 #define LTK_R(j, e) io.rows[(long)(((j) - 1) * 7 + (e)) * io.sr]
+#define LTK_STORE_ROW(j, W)                                                                                   \
+    do {                                                                                                      \
+        LTK_R(j, 0) = (W).a; LTK_R(j, 1) = (W).b; LTK_R(j, 2) = (W).c; LTK_R(j, 3) = (W).e1;                   \
+        LTK_R(j, 4) = (W).e2; LTK_R(j, 5) = (W).zx; LTK_R(j, 6) = (W).zy;                                      \
+    } while (0)
 
-// The whole solve for one candidate with N >= 5 unique control points.
-LTK_HD void solve(int N, const Io& io)
+// The whole solve for one candidate with N >= 5 unique control points.  point(j, x, y) yields control point j
+// (0-based, unique points only).
+//
+// Schedule of the forward pass.  Per data row `it` FITPACK performs three band rotations (into rows it, it+1,
+// it+2) and, in our fused order, the two wrapping rows A and B are rotated through row `it` once it is final.
+// The third band rotation always meets a fresh row (diagonal 0): fpgivs then gives c = 0, s = +-1 exactly, so it is
+// a copy.  The remaining four form two dependency chains per row -- band1(it) -> band2(it) -> band1(it+1) and
+// band1(it) -> A(it) -> B(it) -- which are issued as the pairs  band1(it) || B(it-1)  and  band2(it) || A(it).
+template <class PointFn>
+LTK_HD void solve(int N, const Io& io, PointFn point)
 {
     const int n10 = N - 2;
     // periodic knot extension: t(4 - j) = t(N + 4 - j) - per, t(N + 4 + j) = t(4 + j) + per
@@ -179,99 +255,126 @@ LTK_HD void solve(int N, const Io& io)
         int l = N + 2;
         bspl_at_knot(LTK_T(l - 2), LTK_T(l - 1), LTK_T(l), LTK_T(l + 1), LTK_T(l + 2), h1, h2, h3);
         A.h2[0] = 0.0 + h1; A.h2[1] = 0.0 + h2; A.h1[0] = h3; A.h1[1] = 0.0; A.h1[2] = 0.0;
-        A.x = io.px[(long)(N - 2) * io.sp]; A.y = io.py[(long)(N - 2) * io.sp];
+        point(N - 2, A.x, A.y);
         l = N + 3;
         bspl_at_knot(LTK_T(l - 2), LTK_T(l - 1), LTK_T(l), LTK_T(l + 1), LTK_T(l + 2), h1, h2, h3);
         B.h2[0] = 0.0; B.h2[1] = 0.0 + h1; B.h1[0] = h2; B.h1[1] = h3; B.h1[2] = 0.0;
-        B.x = io.px[(long)(N - 1) * io.sp]; B.y = io.py[(long)(N - 1) * io.sp];
+        point(N - 1, B.x, B.y);
     }
-    Row W0 = {0, 0, 0, 0, 0, 0, 0}, W1 = W0, W2 = W0;
+    Row W0 = {0, 0, 0, 0, 0, 0, 0}, W1 = W0, W2 = W0, Wp = W0;  // rows it, it+1, it+2; Wp = row it-1 awaiting B
     double tm2 = LTK_T(2), tm1 = LTK_T(3), t0 = LTK_T(4), tp1 = LTK_T(5);
     for (int it = 1; it <= n10; ++it) {
         const double tp2 = LTK_T(it + 5);
-        double h1, h2, h3, c, s;
+        double h1, h2, h3, c, s, cw, sw;
         bspl_at_knot(tm2, tm1, t0, tp1, tp2, h1, h2, h3);
         tm2 = tm1; tm1 = t0; t0 = tp1; tp1 = tp2;
-        double x = io.px[(long)(it - 1) * io.sp], y = io.py[(long)(it - 1) * io.sp];
-        if (h1 != 0.0) {
-            givens(h1, W0.a, c, s);
+        double x, y;
+        point(it - 1, x, y);
+        // ---- band1(it) || B(it-1)
+        if (it >= 2 && h1 != 0.0 && B.h1[0] != 0.0) {
+            givens2(h1, W0.a, c, s, B.h1[0], Wp.a, cw, sw);
             rota(c, s, x, W0.zx);
             rota(c, s, y, W0.zy);
             rota(c, s, h2, W0.b);
             rota(c, s, h3, W0.c);
+            wrap_apply(B, Wp, it - 1, n10, cw, sw);
+        } else {
+            if (h1 != 0.0) {
+                givens(h1, W0.a, c, s);
+                rota(c, s, x, W0.zx);
+                rota(c, s, y, W0.zy);
+                rota(c, s, h2, W0.b);
+                rota(c, s, h3, W0.c);
+            }
+            if (it >= 2) wrap_rotate(B, Wp, it - 1, n10);
         }
-        if (h2 != 0.0) {
-            givens(h2, W1.a, c, s);
-            rota(c, s, x, W1.zx);
-            rota(c, s, y, W1.zy);
-            rota(c, s, h3, W1.b);
-        }
-        if (h3 != 0.0) {
-            givens(h3, W2.a, c, s);
-            rota(c, s, x, W2.zx);
-            rota(c, s, y, W2.zy);
-        }
+        if (it >= 2) LTK_STORE_ROW(it - 1, Wp);
         // row `it` is final for the band part; its entries beyond column n10 belong to the periodic block
         if (it == n10 - 1) W0.e1 = W0.c;
         if (it == n10) { W0.e1 = W0.b; W0.e2 = W0.c; }
-        wrap_rotate(A, W0, it, n10);
-        wrap_rotate(B, W0, it, n10);
-        LTK_R(it, 0) = W0.a; LTK_R(it, 1) = W0.b; LTK_R(it, 2) = W0.c; LTK_R(it, 3) = W0.e1;
-        LTK_R(it, 4) = W0.e2; LTK_R(it, 5) = W0.zx; LTK_R(it, 6) = W0.zy;
-        W0 = W1; W1 = W2;
+        // ---- band2(it) || A(it)
+        if (h2 != 0.0 && A.h1[0] != 0.0) {
+            givens2(h2, W1.a, c, s, A.h1[0], W0.a, cw, sw);
+            rota(c, s, x, W1.zx);
+            rota(c, s, y, W1.zy);
+            rota(c, s, h3, W1.b);
+            wrap_apply(A, W0, it, n10, cw, sw);
+        } else {
+            if (h2 != 0.0) {
+                givens(h2, W1.a, c, s);
+                rota(c, s, x, W1.zx);
+                rota(c, s, y, W1.zy);
+                rota(c, s, h3, W1.b);
+            }
+            wrap_rotate(A, W0, it, n10);
+        }
+        // ---- band3(it): row it+2 is fresh (a = 0, z = 0), so fpgivs yields dd = |h3|, c = 0, s = h3 / |h3|
+        if (h3 != 0.0) {
+            const double sg = (h3 < 0.0) ? -1.0 : 1.0;
+            W2.a = fabs(h3);
+            W2.zx = 0.0 + sg * x;
+            W2.zy = 0.0 + sg * y;
+        }
+        Wp = W0; W0 = W1; W1 = W2;
         W2.a = W2.b = W2.c = W2.e1 = W2.e2 = W2.zx = W2.zy = 0.0;
     }
+    wrap_rotate(B, Wp, n10, n10);
+    LTK_STORE_ROW(n10, Wp);
     // W0 = row N-1: a2(N-1, 1..2) = (a, b); W1 = row N: a2(N, 2) = a
     wrap_tail(A, W0, W1);
     wrap_tail(B, W0, W1);
-    // fpbacp
+    // fpbacp; the coefficients go to cx, cy (c(N + q) = c(q), q = 1..3)
+#define LTK_CX(i) io.cx[(long)((i) - 1) * io.sc]
+#define LTK_CY(i) io.cy[(long)((i) - 1) * io.sc]
     const double cNx = fdiv(W1.zx, W1.a), cNy = fdiv(W1.zy, W1.a);
     const double cMx = fdiv(W0.zx - cNx * W0.b, W0.a), cMy = fdiv(W0.zy - cNy * W0.b, W0.a);
+    LTK_CX(N) = cNx; LTK_CY(N) = cNy; LTK_CX(N - 1) = cMx; LTK_CY(N - 1) = cMy;
     double c1x = 0, c2x = 0, c1y = 0, c2y = 0;  // c(i+1), c(i+2)
+    // the next row is fetched before the current one's divisions: the loads do not wait for the chain
+    double ra = LTK_R(n10, 0), rb = LTK_R(n10, 1), rc = LTK_R(n10, 2), re1 = LTK_R(n10, 3), re2 = LTK_R(n10, 4),
+           rzx = LTK_R(n10, 5), rzy = LTK_R(n10, 6);
     for (int i = n10; i >= 1; --i) {
-        const double a = LTK_R(i, 0), b = LTK_R(i, 1), cc = LTK_R(i, 2), e1 = LTK_R(i, 3), e2 = LTK_R(i, 4);
-        double sx = LTK_R(i, 5), sy = LTK_R(i, 6);
+        const double a = ra, b = rb, cc = rc, e1 = re1, e2 = re2;
+        double sx = rzx, sy = rzy;
+        if (i > 1) {
+            ra = LTK_R(i - 1, 0); rb = LTK_R(i - 1, 1); rc = LTK_R(i - 1, 2); re1 = LTK_R(i - 1, 3);
+            re2 = LTK_R(i - 1, 4); rzx = LTK_R(i - 1, 5); rzy = LTK_R(i - 1, 6);
+        }
         sx = sx - cMx * e1; sx = sx - cNx * e2;
         sy = sy - cMy * e1; sy = sy - cNy * e2;
         if (i <= n10 - 1) { sx = sx - c1x * b; sy = sy - c1y * b; }
         if (i <= n10 - 2) { sx = sx - c2x * cc; sy = sy - c2y * cc; }
-        sx = fdiv(sx, a); sy = fdiv(sy, a);
+        fdiv2(sx, a, sy, a, sx, sy);
         c2x = c1x; c2y = c1y; c1x = sx; c1y = sy;
-        LTK_R(i, 5) = sx; LTK_R(i, 6) = sy;  // c(i) takes the place of z(i)
+        LTK_CX(i) = sx; LTK_CY(i) = sy;
     }
-#define LTK_CX(i) ((i) > N ? LTK_CX0((i) - N) : LTK_CX0(i))
-#define LTK_CX0(i) ((i) == N ? cNx : (i) == N - 1 ? cMx : LTK_R(i, 5))
-#define LTK_CY(i) ((i) > N ? LTK_CY0((i) - N) : LTK_CY0(i))
-#define LTK_CY0(i) ((i) == N ? cNy : (i) == N - 1 ? cMy : LTK_R(i, 6))
-    if (io.cx) {
-        for (int i = 1; i <= N + 3; ++i) {
-            io.cx[(long)(i - 1) * io.sc] = LTK_CX(i);
-            io.cy[(long)(i - 1) * io.sc] = LTK_CY(i);
-        }
-    }
+    for (int q = 1; q <= 3; ++q) { LTK_CX(N + q) = LTK_CX(q); LTK_CY(N + q) = LTK_CY(q); }
     // splder: wrk1(i) = 3 (c(i+1) - c(i)) / (t(i+4) - t(i+1)),  wrk2(i) = 2 (wrk1(i+1) - wrk1(i)) / (t(i+4) - t(i+2))
     double px_ = LTK_CX(1), py_ = LTK_CY(1), w1px = 0, w1py = 0;
+    double nx = LTK_CX(2), ny = LTK_CY(2);
     for (int i = 1; i <= N + 2; ++i) {
-        const double nx = LTK_CX(i + 1), ny = LTK_CY(i + 1);
-        const double t4 = LTK_T(i + 4);
-        const double fac = t4 - LTK_T(i + 1);
-        const double w1x = fdiv(3.0 * (nx - px_), fac), w1y = fdiv(3.0 * (ny - py_), fac);
+        const double cx1 = nx, cy1 = ny;
+        if (i <= N + 1) { nx = LTK_CX(i + 2); ny = LTK_CY(i + 2); }  // fetched one iteration ahead
+        const double fac = LTK_T(i + 4) - LTK_T(i + 1);
+        double w1x, w1y;
+        fdiv2(3.0 * (cx1 - px_), fac, 3.0 * (cy1 - py_), fac, w1x, w1y);
         io.w1x[(long)(i - 1) * io.sw] = w1x;
         io.w1y[(long)(i - 1) * io.sw] = w1y;
         if (i >= 2) {  // wrk2(i-1) from wrk1(i-1), wrk1(i): knots t(i+3), t(i+1)
             const double fac2 = LTK_T(i + 3) - LTK_T(i + 1);
-            io.w2x[(long)(i - 2) * io.sw] = fdiv(2.0 * (w1x - w1px), fac2);
-            io.w2y[(long)(i - 2) * io.sw] = fdiv(2.0 * (w1y - w1py), fac2);
+            double w2x, w2y;
+            fdiv2(2.0 * (w1x - w1px), fac2, 2.0 * (w1y - w1py), fac2, w2x, w2y);
+            io.w2x[(long)(i - 2) * io.sw] = w2x;
+            io.w2y[(long)(i - 2) * io.sw] = w2y;
         }
-        w1px = w1x; w1py = w1y; px_ = nx; py_ = ny;
+        w1px = w1x; w1py = w1y; px_ = cx1; py_ = cy1;
     }
 #undef LTK_CX
-#undef LTK_CX0
 #undef LTK_CY
-#undef LTK_CY0
 }
 #undef LTK_T
 #undef LTK_R
+#undef LTK_STORE_ROW
 
 // One spline interval t(l) <= x < t(l+1) as the sample loop needs it (splder + fpbspl of degree 2 and 1).
 struct __align__(16) FitInterval {

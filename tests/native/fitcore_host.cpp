@@ -23,12 +23,11 @@ int fitcore_solve(int N, const double* px, const double* py, const double* u, do
     std::vector<double> rows((size_t)7 * N, 0.0);
     for (int j = 0; j <= N; ++j) t[j + 3] = u[j];
     Io io;
-    io.px = px; io.py = py; io.sp = 1;
     io.t = t; io.st = 1;
     io.rows = rows.data(); io.sr = 1;
     io.cx = cx; io.cy = cy; io.sc = 1;
     io.w1x = w1x; io.w1y = w1y; io.w2x = w2x; io.w2y = w2y; io.sw = 1;
-    solve(N, io);
+    solve(N, io, [&](int j, double& x, double& y) { x = px[j]; y = py[j]; });
     return 0;
 }
 
