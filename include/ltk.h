@@ -183,6 +183,18 @@ int ltk_path_eval(int device, const double *d_xy, const double *d_knots, int m, 
                   int64_t n, double *d_x, double *d_y, double *d_dx, double *d_dy, double *d_ddx,
                   double *d_ddy, double *d_k_signed, double *d_gamma2, void *stream);
 
+/* The same facade in SciPy FITPACK's own arithmetic (see LTK_SPLINE_FITPACK), closed or open:
+ * splprep(d_xy, u=d_knots, k=3, s=0, per=closed) (path.py:25) -- fpclos for a closed path (m-1 unique points, last
+ * column ignored; m >= 6), fppara with the not-a-knot knot vector for an open one (m >= 4; path.py:25 with
+ * closed = False, reached from trajectory.py:189-192) -- and splev(d_u, tck, der=0|1|2) (path.py:33, :51-54).
+ * Knots, coefficients, positions and derivatives come out bit-equal to SciPy's; the curvature uses a correctly
+ * rounded x**1.5.  d_t [m + 6 closed | m + 4 open] and d_c [2][m + 2 closed | m open] receive the tck that
+ * Path.spline holds in the reference (either may be NULL; n may be 0). */
+int ltk_path_eval_fitpack(int device, const double *d_xy, const double *d_knots, int m, int closed,
+                          const double *d_u, int64_t n, double *d_x, double *d_y, double *d_dx, double *d_dy,
+                          double *d_ddx, double *d_ddy, double *d_k_signed, double *d_gamma2, double *d_t,
+                          double *d_c, void *stream);
+
 /* VelocityProfile facade (velocity.py:9-76) for caller-supplied samples: d_s, d_k [n];
  * s_max < 0 means an open path (s_max=None in the reference). Outputs [n] each; d_vacc and d_vdec are
  * required (they are the sweep state), d_vlocal and d_v may be NULL. */

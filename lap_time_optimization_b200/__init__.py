@@ -9,7 +9,7 @@ from ._native import LtkError, LtkUnavailable  # noqa: F401
 from .track import Track  # noqa: F401
 from .vehicle import Vehicle  # noqa: F401
 from .vehicleMX5 import VehicleMX5  # noqa: F401
-from .path import Path  # noqa: F401
+from .path import Path, default_spline, set_default_spline  # noqa: F401
 from .velocity import VelocityProfile  # noqa: F401
 from .evaluator import LapTimeEvaluator  # noqa: F401
 from .trajectory import Trajectory  # noqa: F401

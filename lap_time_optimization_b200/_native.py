@@ -57,6 +57,7 @@ SIGNATURES = {
     "ltk_profile": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ltk_topk": (C.c_int, [_vp, _vp, C.c_int64, C.c_int64, C.c_int, _vp, _vp, _vp]),
     "ltk_path_eval": (C.c_int, [C.c_int, _vp, _vp, C.c_int, _vp, C.c_int64] + [_vp] * 9),
+    "ltk_path_eval_fitpack": (C.c_int, [C.c_int, _vp, _vp, C.c_int, C.c_int, _vp, C.c_int64] + [_vp] * 11),
     "ltk_velocity_profile": (C.c_int, [C.c_int, C.POINTER(LtkVehicle), _vp, _vp, C.c_int64, C.c_double,
                                        _vp, _vp, _vp, _vp, _vp]),
     "ltk_version": (C.c_int, []),

@@ -342,7 +342,7 @@ cudaError_t launch_k1b(const K1Args& a, size_t smem, cudaStream_t st)
 
 // K1b (ltk_spline.cuh): G candidates per CTA, T threads
 struct K1FConfig {
-    int G, threads;
+    int G, threads, staged;
     size_t smem;
 };
 
@@ -351,23 +351,27 @@ bool pick_k1f(const ltk_ctx* ctx, K1FConfig* out)
     const bool fitp = ctx->spline_mode == LTK_SPLINE_FITPACK;
     if (ctx->k1_mode == 1 && !fitp) return false;  // LTK_K1=old: the previous K1a + K1b pair (A/B reference)
     if ((fitp ? k1af_smem_bytes(ctx->N) : k1a_smem_bytes(ctx->N)) > ctx->smem_optin) return false;
-    const int cand[7][2] = {{4, 256}, {4, 128}, {8, 256}, {2, 128}, {2, 64}, {1, 256}, {1, 128}};  // measured order
-    for (int i = 0; i < 7; ++i) {
-        int G = cand[i][0], T = cand[i][1];
+    // measured order.  The shared-memory tile (staged) wins while four candidates' rows fit; beyond that
+    // (ns > ~6,600) the two-pass variant at G = 4 does (profiles/README.md, ns = 10,001).  G = 1, 2 tiles are
+    // only reachable through LTK_K1_G.
+    const int cand[8][3] = {{4, 256, 1}, {4, 128, 1}, {8, 256, 1}, {4, 256, 0}, {2, 128, 1}, {2, 64, 1}, {1, 256, 1}, {1, 128, 1}};
+    for (int i = 0; i < 8; ++i) {
+        int G = cand[i][0], T = cand[i][1], staged = cand[i][2];
         if (ctx->k1_g_override > 0 && G != ctx->k1_g_override) continue;
         if (ctx->k1_threads_override > 0 && T != ctx->k1_threads_override) continue;
-        size_t s = k1f_smem_bytes(G, T, ctx->N, ctx->ns, fitp);
-        if (s <= ctx->smem_optin) { out->G = G; out->threads = T; out->smem = s; return true; }
+        if (ctx->k1_staged_override >= 0 && staged != ctx->k1_staged_override) continue;
+        size_t s = k1f_smem_bytes(G, T, ctx->N, ctx->ns, fitp, staged != 0);
+        if (s <= ctx->smem_optin) { out->G = G; out->threads = T; out->staged = staged; out->smem = s; return true; }
     }
     return false;
 }
 
-template <int G, int T, int MINB, bool FIT>
+template <int G, int T, int MINB, bool FIT, bool STAGED = true>
 cudaError_t launch_k1f(const K1Args& a, const FitArgs& fa, size_t smem, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(k1b_samples<G, T, MINB, FIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k1b_samples<G, T, MINB, FIT, STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k1b_samples<G, T, MINB, FIT><<<(unsigned)(a.Bp / G), T, smem, st>>>(a, fa);
+    k1b_samples<G, T, MINB, FIT, STAGED><<<(unsigned)(a.Bp / G), T, smem, st>>>(a, fa);
     g_launches.fetch_add(1);
     return cudaGetLastError();
 }
@@ -375,6 +379,7 @@ cudaError_t launch_k1f(const K1Args& a, const FitArgs& fa, size_t smem, cudaStre
 template <bool FIT>
 cudaError_t launch_k1f_cfg(const K1FConfig& c, const K1Args& a, const FitArgs& fa, cudaStream_t st)
 {
+    if (!c.staged) return launch_k1f<4, 256, 4, FIT, false>(a, fa, c.smem, st);
     if (c.G == 1 && c.threads == 256) return launch_k1f<1, 256, 2, FIT>(a, fa, c.smem, st);
     if (c.G == 1) return launch_k1f<1, 128, 4, FIT>(a, fa, c.smem, st);
     if (c.G == 2 && c.threads == 128) return launch_k1f<2, 128, 8, FIT>(a, fa, c.smem, st);
@@ -1082,6 +1087,25 @@ int ltk_path_eval(int device, const double* d_xy, const double* d_knots, int m, 
     g_launches.fetch_add(1);
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail(nullptr, LTK_E_CUDA, "path_eval_kernel", e);
+    return LTK_OK;
+}
+
+int ltk_path_eval_fitpack(int device, const double* d_xy, const double* d_knots, int m, int closed, const double* d_u,
+                          int64_t n, double* d_x, double* d_y, double* d_dx, double* d_dy, double* d_ddx, double* d_ddy,
+                          double* d_k_signed, double* d_gamma2, double* d_t, double* d_c, void* stream)
+{
+    if (!d_xy || !d_knots || (!d_u && n > 0) || n < 0) return fail(nullptr, LTK_E_ARG, "null or negative argument");
+    if (closed ? m < 6 : m < 4)
+        return fail(nullptr, LTK_E_UNSUPPORTED, "FITPACK arithmetic needs 5 unique points (closed) or 4 points (open)");
+    DeviceGuard guard(device);
+    size_t smem = sizeof(double) * path_fit_smem_doubles(m, closed);
+    cudaError_t e = cudaFuncSetAttribute(path_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(nullptr, LTK_E_UNSUPPORTED, "path too long for shared memory", e);
+    PathFitArgs a{d_xy, d_knots, m, closed ? 1 : 0, d_u, n, d_x, d_y, d_dx, d_dy, d_ddx, d_ddy, d_k_signed, d_gamma2, d_t, d_c};
+    path_fit_kernel<<<1, 256, smem, static_cast<cudaStream_t>(stream)>>>(a);
+    g_launches.fetch_add(1);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(nullptr, LTK_E_CUDA, "path_fit_kernel", e);
     return LTK_OK;
 }
 

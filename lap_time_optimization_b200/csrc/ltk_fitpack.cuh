@@ -55,4 +55,92 @@ __global__ void __launch_bounds__(K1AF_THREADS) k1a_fitpack(K1Args a, FitArgs f)
     for (int l = 0; l < N + 7; ++l) f.t[(size_t)l * a.Bp + b] = TK[l * 32 + lane];
 }
 
+// ------------------------------------------------------------------------------------------------
+// Path facade in FITPACK arithmetic (path.py:17-77 for ONE path): splprep(controls, u=dists, k=3, s=0, per=closed)
+// by thread 0 -- the periodic fpclos solve (fit::solve) or the open not-a-knot one (fit::solve_open) -- then
+// splev(der = 0 | 1 | 2) at the caller's parameters by all threads, curvature in numpy's operation order.
+// Everything lives in shared memory: t | cx | cy | w1x | w1y | w2x | w2y | scratch.
+// ------------------------------------------------------------------------------------------------
+struct PathFitArgs {
+    const double* xy;     // [2][m]
+    const double* knots;  // [m]
+    int m, closed;
+    const double* u;
+    long long n;
+    double *x, *y, *dx, *dy, *ddx, *ddy, *k, *gamma2;
+    double* t_out;  // [m + 6] closed | [m + 4] open, or nullptr
+    double* c_out;  // [2][m + 2] closed | [2][m] open, or nullptr
+};
+
+__host__ __device__ inline size_t path_fit_smem_doubles(int m, int closed)
+{
+    const size_t n = closed ? m + 6 : m + 4;
+    return n + 6 * n + (closed ? 7 * (size_t)(m - 1) + 2 * (size_t)m : 6 * (size_t)m);
+}
+
+__global__ void __launch_bounds__(256) path_fit_kernel(PathFitArgs a)
+{
+    extern __shared__ __align__(16) double smp[];
+    __shared__ double red[256];
+    const int m = a.m, tid = threadIdx.x;
+    const int n = a.closed ? m + 6 : m + 4, nc = n - 4;
+    double* T = smp;
+    double* CX = T + n;
+    double* CY = CX + n;
+    double* W1X = CY + n;
+    double* W1Y = W1X + n;
+    double* W2X = W1Y + n;
+    double* W2Y = W2X + n;
+    double* SCR = W2Y + n;
+    if (tid == 0) {
+        if (a.closed) {
+            const int N = m - 1;
+            double* PX = SCR + 7 * N;
+            double* PY = PX + m;
+            for (int j = 0; j < N; ++j) { PX[j] = a.xy[j]; PY[j] = a.xy[m + j]; }
+            for (int j = 0; j <= N; ++j) T[j + 3] = a.knots[j];
+            fit::Io io;
+            io.t = T; io.st = 1;
+            io.rows = SCR; io.sr = 1;
+            io.cx = CX; io.cy = CY; io.sc = 1;
+            io.w1x = W1X; io.w1y = W1Y; io.w2x = W2X; io.w2y = W2Y; io.sw = 1;
+            fit::solve(N, io, [&](int j, double& x, double& y) { x = PX[j]; y = PY[j]; });
+        } else {
+            double* A = SCR;         // [4 m]
+            double* Z = A + 4 * m;   // [2 m]
+            fit::solve_open(m, a.knots, a.xy, a.xy + m, T, A, Z, CX, CY);
+            fit::der_coeffs(T, n, CX, W1X, W2X);
+            fit::der_coeffs(T, n, CY, W1Y, W2Y);
+        }
+    }
+    __syncthreads();
+    if (a.t_out) for (int i = tid; i < n; i += blockDim.x) a.t_out[i] = T[i];
+    if (a.c_out) for (int i = tid; i < nc; i += blockDim.x) { a.c_out[i] = CX[i]; a.c_out[nc + i] = CY[i]; }
+    double g2 = 0.0;
+    for (long long e = tid; e < a.n; e += blockDim.x) {
+        const double s = a.u[e];
+        const int l = fit::find_interval(T, n, s);
+        const double dx = fit::splev_at(T, W1X, 1, s, l), dy = fit::splev_at(T, W1Y, 1, s, l);
+        const double ddx = fit::splev_at(T, W2X, 2, s, l), ddy = fit::splev_at(T, W2Y, 2, s, l);
+        const double cross = dx * ddy - dy * ddx;       // path.py:58 in numpy's operation order
+        const double n2 = dx * dx + dy * dy;
+        const double k = cross / fit::pow15(n2);
+        if (a.x) a.x[e] = fit::splev_at(T, CX, 0, s, l);
+        if (a.y) a.y[e] = fit::splev_at(T, CY, 0, s, l);
+        if (a.dx) a.dx[e] = dx;
+        if (a.dy) a.dy[e] = dy;
+        if (a.ddx) a.ddx[e] = ddx;
+        if (a.ddy) a.ddy[e] = ddy;
+        if (a.k) a.k[e] = k;
+        g2 += k * k;
+    }
+    red[tid] = g2;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o) red[tid] += red[tid + o];
+        __syncthreads();
+    }
+    if (tid == 0 && a.gamma2) a.gamma2[0] = red[0];
+}
+
 }  // namespace ltk

@@ -157,6 +157,34 @@ LTK_HD void bspl_at_knot(double tm2, double tm1, double t0, double tp1, double t
     h3 = fb * (t0 - tm1);
 }
 
+// The same in two halves, so that the three dependent divisions of the NEXT data row can be issued inside the
+// basic blocks of the current row's two rotation stages (a warp issues in order: only instructions of one
+// block interleave).  bspl_begin: degrees 1 and 2; bspl_end: degree 3.
+struct BsplMid {
+    double a, g1, g2;
+};
+LTK_HD BsplMid bspl_begin(double tm1, double t0, double tp1)
+{
+    BsplMid m;
+    m.a = tp1 - t0;
+    double f = fdiv(1.0, m.a);
+    m.g1 = f * m.a;
+    f = fdiv(m.g1, tp1 - tm1);
+    m.g1 = f * m.a;
+    m.g2 = f * (t0 - tm1);
+    return m;
+}
+LTK_HD void bspl_end(const BsplMid& m, double tm2, double tm1, double t0, double tp1, double tp2, double& h1, double& h2,
+                     double& h3)
+{
+    double fa, fb;
+    fdiv2(m.g1, tp1 - tm2, m.g2, tp2 - tm1, fa, fb);
+    h1 = fa * m.a;
+    h2 = fa * (t0 - tm2);
+    h2 = h2 + fb * (tp2 - t0);
+    h3 = fb * (t0 - tm1);
+}
+
 struct Row {  // one row of the triangular factor: band part a1(j, 1..3), periodic part a2(j, 1..2), z(j) per dim
     double a, b, c, e1, e2, zx, zy;
 };
@@ -262,23 +290,28 @@ LTK_HD void solve(int N, const Io& io, PointFn point)
         point(N - 1, B.x, B.y);
     }
     Row W0 = {0, 0, 0, 0, 0, 0, 0}, W1 = W0, W2 = W0, Wp = W0;  // rows it, it+1, it+2; Wp = row it-1 awaiting B
-    double tm2 = LTK_T(2), tm1 = LTK_T(3), t0 = LTK_T(4), tp1 = LTK_T(5);
+    // software pipeline: the B-spline row and the control point of data row it+1 are produced during row it
+    double tm2 = LTK_T(2), tm1 = LTK_T(3), t0 = LTK_T(4), tp1 = LTK_T(5), tp2 = LTK_T(6);
+    double hn1, hn2, hn3, xn, yn;
+    bspl_at_knot(tm2, tm1, t0, tp1, tp2, hn1, hn2, hn3);
+    point(0, xn, yn);
     for (int it = 1; it <= n10; ++it) {
-        const double tp2 = LTK_T(it + 5);
-        double h1, h2, h3, c, s, cw, sw;
-        bspl_at_knot(tm2, tm1, t0, tp1, tp2, h1, h2, h3);
-        tm2 = tm1; tm1 = t0; t0 = tp1; tp1 = tp2;
-        double x, y;
-        point(it - 1, x, y);
-        // ---- band1(it) || B(it-1)
+        double h1 = hn1, h2 = hn2, h3 = hn3, x = xn, y = yn, c, s, cw, sw;
+        // operands of data row it+1 (row n10+1 = A exists as well: the values are simply not used after the loop)
+        tm2 = tm1; tm1 = t0; t0 = tp1; tp1 = tp2; tp2 = LTK_T(it + 6);
+        point(it, xn, yn);
+        BsplMid mid;
+        // ---- band1(it) || B(it-1)  [+ first half of the next B-spline row]
         if (it >= 2 && h1 != 0.0 && B.h1[0] != 0.0) {
             givens2(h1, W0.a, c, s, B.h1[0], Wp.a, cw, sw);
+            mid = bspl_begin(tm1, t0, tp1);
             rota(c, s, x, W0.zx);
             rota(c, s, y, W0.zy);
             rota(c, s, h2, W0.b);
             rota(c, s, h3, W0.c);
             wrap_apply(B, Wp, it - 1, n10, cw, sw);
         } else {
+            mid = bspl_begin(tm1, t0, tp1);
             if (h1 != 0.0) {
                 givens(h1, W0.a, c, s);
                 rota(c, s, x, W0.zx);
@@ -292,14 +325,16 @@ LTK_HD void solve(int N, const Io& io, PointFn point)
         // row `it` is final for the band part; its entries beyond column n10 belong to the periodic block
         if (it == n10 - 1) W0.e1 = W0.c;
         if (it == n10) { W0.e1 = W0.b; W0.e2 = W0.c; }
-        // ---- band2(it) || A(it)
+        // ---- band2(it) || A(it)  [+ second half of the next B-spline row]
         if (h2 != 0.0 && A.h1[0] != 0.0) {
             givens2(h2, W1.a, c, s, A.h1[0], W0.a, cw, sw);
+            bspl_end(mid, tm2, tm1, t0, tp1, tp2, hn1, hn2, hn3);
             rota(c, s, x, W1.zx);
             rota(c, s, y, W1.zy);
             rota(c, s, h3, W1.b);
             wrap_apply(A, W0, it, n10, cw, sw);
         } else {
+            bspl_end(mid, tm2, tm1, t0, tp1, tp2, hn1, hn2, hn3);
             if (h2 != 0.0) {
                 givens(h2, W1.a, c, s);
                 rota(c, s, x, W1.zx);
@@ -444,6 +479,120 @@ LTK_HD double curvature_at(const FitInterval& v, double x, double& dx, double& d
     const double cross = dx * ddy - dy * ddx;
     const double n2 = dx * dx + dy * dy;
     return fabs(fdiv(cross, pow15(n2)));
+}
+
+// ---- general evaluation (Path facade): splev / splder at one point of any cubic spline (t, c) ---------------------
+// fpbspl for degree k <= 3 at t(l) <= x < t(l+1); t is contiguous, FITPACK's t(l) = t[l - 1]; h[0 .. k]
+LTK_HD void bspl(const double* t, int k, double x, int l, double* h)
+{
+    double hh[4];
+    h[0] = 1.0;
+    for (int j = 1; j <= k; ++j) {
+        for (int i = 0; i < j; ++i) hh[i] = h[i];
+        h[0] = 0.0;
+        for (int i = 1; i <= j; ++i) {
+            const double tli = t[l + i - 1], tlj = t[l + i - j - 1];
+            if (tli == tlj) {
+                h[i] = 0.0;
+                continue;
+            }
+            const double f = fdiv(hh[i - 1], tli - tlj);
+            h[i - 1] = h[i - 1] + f * (tli - x);
+            h[i] = f * (x - tlj);
+        }
+    }
+}
+
+// splder's coefficient passes for nu = 1 and 2: w1 [n - 5], w2 [n - 6] from c [n - 4]
+LTK_HD void der_coeffs(const double* t, int n, const double* c, double* w1, double* w2)
+{
+    const int nk1 = n - 4;
+    for (int i = 1; i <= nk1 - 1; ++i) {
+        const double fac = t[i + 4 - 1] - t[i + 1 - 1];
+        w1[i - 1] = (fac <= 0.0) ? c[i - 1] : fdiv(3.0 * (c[i] - c[i - 1]), fac);
+    }
+    for (int i = 1; i <= nk1 - 2; ++i) {
+        const double fac = t[i + 4 - 1] - t[i + 2 - 1];
+        w2[i - 1] = (fac <= 0.0) ? w1[i - 1] : fdiv(2.0 * (w1[i] - w1[i - 1]), fac);
+    }
+}
+
+// knot interval of x as splev / splder pick it: the largest l in [4, n - 4] with t(l) <= x (l = 4 below the span)
+LTK_HD int find_interval(const double* t, int n, double x)
+{
+    int lo = 4, hi = n - 4;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (t[mid - 1] <= x) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// value of the nu-th derivative at x in interval l; coef = c (nu = 0), w1 (nu = 1) or w2 (nu = 2)
+LTK_HD double splev_at(const double* t, const double* coef, int nu, double x, int l)
+{
+    double h[4];
+    bspl(t, 3 - nu, x, l, h);
+    double sp = 0.0;
+    for (int j = 0; j <= 3 - nu; ++j) sp = sp + coef[l - 4 + j] * h[j];
+    return sp;
+}
+
+// Open interpolating cubic spline through m >= 4 points (splprep(..., per=0, s=0): fppara with the not-a-knot knot
+// vector, banded Givens QR, fpback); reference path.py:25 with closed = False.  u [m], px, py [m] -> t [m + 4],
+// cx, cy [m]; scratch a [4 m], z [2 m].  Contiguous arrays, one thread.
+LTK_HD void solve_open(int m, const double* u, const double* px, const double* py, double* t, double* a, double* z,
+                       double* cx, double* cy)
+{
+    const int n = m + 4, nk1 = m;
+    for (int i = 0; i < 4; ++i) { t[i] = u[0]; t[nk1 + i] = u[m - 1]; }
+    for (int q = 0; q < m - 4; ++q) t[4 + q] = u[2 + q];
+    for (int i = 0; i < 4 * m; ++i) a[i] = 0.0;
+    for (int i = 0; i < 2 * m; ++i) z[i] = 0.0;
+#define LTK_A(j, e) a[((j) - 1) * 4 + (e) - 1]
+    int l = 4;
+    for (int it = 1; it <= m; ++it) {
+        const double ui = u[it - 1];
+        double x = px[it - 1], y = py[it - 1];
+        while (!(ui < t[l] || l == nk1)) ++l;
+        double h[4];
+        bspl(t, 3, ui, l, h);
+        int j = l - 4;
+        for (int i = 1; i <= 4; ++i) {
+            ++j;
+            const double piv = h[i - 1];
+            if (piv == 0.0) continue;
+            double c, s;
+            givens(piv, LTK_A(j, 1), c, s);
+            rota(c, s, x, z[j - 1]);
+            rota(c, s, y, z[m + j - 1]);
+            if (i == 4) break;
+            int i2 = 1;
+            for (int i1 = i + 1; i1 <= 4; ++i1) {
+                ++i2;
+                rota(c, s, h[i1 - 1], LTK_A(j, i2));
+            }
+        }
+    }
+    for (int d = 0; d < 2; ++d) {  // fpback
+        const double* zz = z + d * m;
+        double* cc = d ? cy : cx;
+        cc[nk1 - 1] = fdiv(zz[nk1 - 1], LTK_A(nk1, 1));
+        int i = nk1 - 1;
+        for (int j = 2; j <= nk1; ++j) {
+            double store = zz[i - 1];
+            const int i1 = j <= 3 ? j - 1 : 3;
+            int mm = i;
+            for (int q = 1; q <= i1; ++q) {
+                ++mm;
+                store = store - cc[mm - 1] * LTK_A(i, q + 1);
+            }
+            cc[i - 1] = fdiv(store, LTK_A(i, 1));
+            --i;
+        }
+    }
+#undef LTK_A
+    (void)n;
 }
 
 }  // namespace fit

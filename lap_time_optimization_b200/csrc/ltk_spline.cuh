@@ -40,9 +40,10 @@ __host__ __device__ inline size_t k1f_scratch_doubles(int G, int N, bool fitpack
     return (size_t)(fitpack ? 5 * N + 13 : 5 * N + 1) * G;
 }
 
-__host__ __device__ inline size_t k1f_smem_bytes(int G, int threads, int N, int ns, bool fitpack = false)
+__host__ __device__ inline size_t k1f_smem_bytes(int G, int threads, int N, int ns, bool fitpack = false,
+                                                 bool staged = true)
 {
-    size_t tile = (size_t)(ns - 1) * G, scr = k1f_scratch_doubles(G, N, fitpack);
+    size_t tile = staged ? (size_t)(ns - 1) * G : 0, scr = k1f_scratch_doubles(G, N, fitpack);
     size_t bytes = (size_t)N * G * (fitpack ? sizeof(fit::FitInterval) : sizeof(Interval));  // interval records [N][G]
     bytes += (tile > scr ? tile : scr) * sizeof(double);             // curvature tile | scratch
     bytes += (size_t)(N + 1) * G * sizeof(int) + 8;                  // first sample index of each interval (+ alignment)
@@ -182,7 +183,11 @@ __global__ void __launch_bounds__(K1A_THREADS, 4) k1a_solve(K1Args a)
 // ------------------------------------------------------------------------------------------------
 // FIT = true: the records and the per-sample arithmetic of the FITPACK mode (ltk_fitpack_core.cuh); the
 // hand-off arrays are then K1a-F's knots t [N+7] and derivative coefficients wrk1 [N+2], wrk2 [N+1] per coordinate.
-template <int G, int T, int MINB, bool FIT>
+// STAGED = false: two passes over the samples instead of the shared-memory tile -- the first finds the rotation,
+// the second recomputes the curvatures and writes them straight to their rotated rows.  Twice the arithmetic,
+// but the kernel keeps G = 4 and full occupancy when the tile would not fit (ns = 10,001: 8.0 ms with the tile at
+// G = 2 and one CTA per SM against 3.4 ms for the old two-pass kernel).
+template <int G, int T, int MINB, bool FIT, bool STAGED>
 __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a, FitArgs fa)
 {
     static_assert(32 % G == 0 && T % 32 == 0, "lanes split evenly over the candidates of a CTA");
@@ -192,8 +197,8 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a, FitArgs fa)
     using Rec = typename std::conditional<FIT, fit::FitInterval, Interval>::type;
     Rec* REC = reinterpret_cast<Rec*>(smraw);
     double* KT = reinterpret_cast<double*>(REC + NG);
-    const size_t tile = (size_t)n * G, scr = k1f_scratch_doubles(G, N, FIT);
-    int* IB = reinterpret_cast<int*>(KT + (tile > scr ? tile : scr));   // [N+1][G]
+    const size_t tile = STAGED ? (size_t)n * G : 0, scr = k1f_scratch_doubles(G, N, FIT);
+    int* IB = reinterpret_cast<int*>(KT + ((STAGED && tile > scr) ? tile : scr));   // [N+1][G]
     double* LEN = reinterpret_cast<double*>(IB + (N + 1) * G + (((N + 1) * G) & 1));
     double* RV = LEN + G;                                               // [NW][G]
     int* RI = reinterpret_cast<int*>(RV + NW * G);                      // [NW][G]
@@ -327,21 +332,20 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a, FitArgs fa)
     const int cbase = n / CPT, cextra = n - cbase * CPT;
     const int i0 = c * cbase + min(c, cextra), i1 = i0 + cbase + (c < cextra ? 1 : 0);
     const double step = LEN[g] / (double)(a.ns - 1);
-    double best = -1.0;
-    int bi = 0;
-    if (i0 < i1) {
-        int lo = 0, hi = N - 1;  // interval of sample i0: largest j with IB[j] <= i0
+    // One flat loop per run of samples: every lane of the warp runs the same number of iterations (nested
+    // per-interval loops diverge -- interval boundaries differ from lane to lane -- and ran at 19 of
+    // 32 lanes); the interval switch is an integer test that fires about once per 20 samples.
+    auto walk = [&](int q0, int q1, auto&& sink) {  // curvature at samples q0 .. q1-1 of candidate g
+        if (q0 >= q1) return;
+        int lo = 0, hi = N - 1;  // interval of sample q0: largest j with IB[j] <= q0
         while (lo < hi) {
             const int mid = (lo + hi + 1) >> 1;
-            if (IB[mid * G + g] <= i0) lo = mid; else hi = mid - 1;
+            if (IB[mid * G + g] <= q0) lo = mid; else hi = mid - 1;
         }
-        // One flat loop per chunk: every lane of the warp runs the same number of iterations (nested
-        // per-interval loops diverge -- interval boundaries differ from lane to lane -- and ran at 19 of
-        // 32 lanes); the interval switch is an integer test that fires about once per 20 samples.
         int j = lo;
         Rec v = REC[j * G + g];
         int inext = IB[(j + 1) * G + g];
-        for (int i = i0; i < i1; ++i) {
+        for (int i = q0; i < q1; ++i) {
             while (i >= inext) {
                 ++j;
                 v = REC[j * G + g];
@@ -362,10 +366,15 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a, FitArgs fa)
                 const double n2 = fma(dx, dx, dy * dy);
                 k = ddiv<false>(cross, n2 * dsqrt<false>(n2));
             }
-            KT[(size_t)i * G + g] = k;
-            if (k > best) { best = k; bi = i; }
+            sink(i, k);
         }
-    }
+    };
+    double best = -1.0;
+    int bi = 0;
+    walk(i0, i1, [&](int i, double k) {
+        if constexpr (STAGED) KT[(size_t)i * G + g] = k;
+        if (k > best) { best = k; bi = i; }
+    });
     // first maximum of the curvature == a minimum of v_local (velocity.py:34).  Lanes l, l+G, l+2G, ...
     // hold consecutive chunks of one candidate: fold the upper lanes into the lower ones, lower chunk first
 #pragma unroll
@@ -393,12 +402,28 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a, FitArgs fa)
         const int q0 = ROT[g];
         double* dst = a.kap + tile_base(b0 + g, n);
         float* dst32 = a.kap32 ? a.kap32 + tile_base(b0 + g, n) : nullptr;
-        for (int i = c; i < n; i += CPT) {
-            int q = i + q0;
-            q = (q >= n) ? q - n : q;
-            const double k = KT[(size_t)q * G + g];
-            dst[(size_t)i * TILE] = k;
-            if (dst32) dst32[(size_t)i * TILE] = (float)k;
+        if constexpr (STAGED) {
+            for (int i = c; i < n; i += CPT) {
+                int q = i + q0;
+                q = (q >= n) ? q - n : q;
+                const double k = KT[(size_t)q * G + g];
+                dst[(size_t)i * TILE] = k;
+                if (dst32) dst32[(size_t)i * TILE] = (float)k;
+            }
+        } else {
+            // second pass: this thread's rows i0 .. i1-1 are the samples i0+q0 .. i1+q0-1 (mod n), one wrap at most;
+            // the G candidates of a row are written by adjacent lanes (one 32-byte sector at G = 4)
+            auto put = [&](int row0, int qa, int qb) {
+                walk(qa, qb, [&](int q, double k) {
+                    const size_t r = (size_t)(row0 + (q - qa)) * TILE;
+                    dst[r] = k;
+                    if (dst32) dst32[r] = (float)k;
+                });
+            };
+            const int qa = i0 + q0, qb = i1 + q0;
+            if (qa >= n) put(i0, qa - n, qb - n);
+            else if (qb <= n) put(i0, qa, qb);
+            else { put(i0, qa, n); put(i0 + (n - qa), 0, qb - n); }
         }
     }
 }

@@ -26,8 +26,12 @@ class LapTimeEvaluator:
     SPLINE_MODES = {"tridiagonal": 0, "fitpack": 1}  # LTK_SPLINE_* (include/ltk.h)
 
     def __init__(self, track, vehicle, mode="bayes", ns=None, device=None, max_workspace_bytes=None,
-                 spline="tridiagonal"):
+                 spline=None):
         torch = _device.torch_cuda()
+        if spline is None:
+            from .path import default_spline
+
+            spline = default_spline()
         self.torch = torch
         self.lib = _native.load()
         self.track, self.vehicle, self.mode = track, vehicle, mode

@@ -1,8 +1,14 @@
 """`Path` facade -- same constructor, attributes and methods as the reference's `Path`
-(src/path.py:17-77), evaluated by the CUDA spline kernel (`ltk_path_eval`, include/ltk.h).
+(src/path.py:17-77), evaluated by the CUDA spline kernels (`ltk_path_eval` / `ltk_path_eval_fitpack`,
+include/ltk.h).
 
-The reference delegates to SciPy FITPACK (`splprep(k=3, s=0, per=1)`); the kernel builds the same
-periodic interpolating cubic through the same knots as a cyclic tridiagonal system."""
+The reference delegates to SciPy FITPACK (`splprep(k=3, s=0, per=closed)`).  Two arithmetics build that spline
+here (`lap_time_optimization_b200.set_default_spline`, or the `spline=` argument):
+  "tridiagonal" -- the same periodic interpolating cubic through the same knots as a cyclic tridiagonal system
+                   (closed paths only; curvature within ~1e-13 of SciPy's);
+  "fitpack"     -- FITPACK's own algorithm and operation order (fpclos / fppara Givens QR, splder, fpbspl): knots,
+                   coefficients, positions and derivatives bit-equal to SciPy's, closed and open paths.
+`Path.spline` (the tck tuple the reference keeps) always comes from the second one."""
 from __future__ import annotations
 
 import numpy as np
@@ -15,13 +21,30 @@ def cumulative_distances(points):
     return np.append(0, np.cumsum(np.linalg.norm(np.diff(points, axis=1), axis=0)))
 
 
+_DEFAULT = {"spline": "tridiagonal"}
+
+
+def set_default_spline(mode):
+    """Spline arithmetic used by `Path` objects and `LapTimeEvaluator`s created from now on that do not name one:
+    "tridiagonal" (fastest) or "fitpack" (SciPy FITPACK's own bits; see include/ltk.h LTK_SPLINE_*)."""
+    if mode not in ("tridiagonal", "fitpack"):
+        raise ValueError("spline mode must be 'tridiagonal' or 'fitpack'")
+    _DEFAULT["spline"] = mode
+
+
+def default_spline():
+    return _DEFAULT["spline"]
+
+
 class Path:
-    """Periodic cubic spline through `controls` ([2, m], last column = first for closed paths),
+    """Interpolating cubic spline through `controls` ([2, m]; closed paths: periodic, last column = first),
     parameterised by cumulative chord length."""
 
-    def __init__(self, controls, closed):
+    def __init__(self, controls, closed, spline=None):
         self.controls = controls
         self.closed = closed
+        self._spline_mode = spline
+        self._tck = None
         self.dists = cumulative_distances(controls)
         self.length = self.dists[-1]
         if closed and isinstance(controls, np.ndarray):
@@ -32,15 +55,20 @@ class Path:
 
     # -- device evaluation -----------------------------------------------------------------------
     def _eval(self, u, want):
-        if not self.closed:
-            raise NotImplementedError("the CUDA path kernel handles closed paths only "
-                                      "(open paths occur only in optimise_sectors; out of scope)")
-        return _device.path_eval(self, np.atleast_1d(np.asarray(u, dtype=np.float64)), want)
+        u = np.atleast_1d(np.asarray(u, dtype=np.float64))
+        mode = self._spline_mode or _DEFAULT["spline"]
+        if mode == "fitpack" or not self.closed:  # the tridiagonal kernel is periodic-only
+            return _device.path_eval_fitpack(self, u, want)
+        return _device.path_eval(self, u, want)
 
     @property
     def spline(self):
-        raise AttributeError("Path.spline (a FITPACK tck tuple in the reference) does not exist here: "
-                             "the spline lives on the device; use position()/curvature()/gamma2()")
+        """The tck tuple `(t, [cx, cy], 3)` the reference keeps in `Path.spline` (path.py:25): knots and B-spline
+        coefficients bit-equal to `splprep(controls, u=dists, k=3, s=0, per=closed)[0]`, computed on the GPU."""
+        if self._tck is None:
+            out = _device.path_eval_fitpack(self, np.empty(0), ("tck",))
+            self._tck = (out["t"], [out["cx"], out["cy"]], 3)
+        return self._tck
 
     def position(self, s=None):
         """x-y coordinates at parameters s (path.py:29-34)."""

@@ -58,6 +58,8 @@ def lib():
         _lib.lto_pow15.argtypes = [C.c_double]
         _lib.fpk_clocur.restype = C.c_int
         _lib.fpk_clocur.argtypes = [dp, dp, C.c_int, C.c_int, dp, dp]
+        _lib.fpk_parcur_open.restype = C.c_int
+        _lib.fpk_parcur_open.argtypes = [dp, dp, C.c_int, C.c_int, dp, dp]
         _lib.fpk_splder.restype = None
         _lib.fpk_splder.argtypes = [dp, C.c_int, dp, C.c_int, dp, C.c_int, dp, dp]
     return _lib
@@ -166,6 +168,18 @@ def fitpack_spline(u, xy):
     t, c = np.zeros(n), np.zeros(idim * n)
     pts = np.ascontiguousarray(xy.T.ravel())
     assert lib().fpk_clocur(_p(u), _p(pts), m, idim, _p(t), _p(c)) == n
+    return t, [c[d * n:(d + 1) * n - 4].copy() for d in range(idim)]
+
+
+def fitpack_spline_open(u, xy):
+    """FITPACK open (not-a-knot) interpolating cubic spline: splprep(xy, u=u, k=3, s=0, per=0)."""
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    xy = np.asarray(xy, dtype=np.float64)
+    idim, m = xy.shape
+    n = m + 4
+    t, c = np.zeros(n), np.zeros(idim * n)
+    pts = np.ascontiguousarray(xy.T.ravel())
+    assert lib().fpk_parcur_open(_p(u), _p(pts), m, idim, _p(t), _p(c)) == n
     return t, [c[d * n:(d + 1) * n - 4].copy() for d in range(idim)]
 
 

@@ -279,3 +279,65 @@ void fpk_splder(const double *t0, int n, const double *c0, int nu, const double 
         y[i] = sp;
     }
 }
+
+/* Open interpolating spline of degree 3 through m points (splprep(..., per=0, s=0): parcur -> fppara with the
+ * not-a-knot knot vector t = [u_1 x4, u_3 .. u_{m-2}, u_m x4]; /root/reference/src/path.py:25 with closed = False,
+ * reached from trajectory.py:189-192).  Row-by-row Givens QR of the banded collocation matrix, fpback.
+ * Outputs t[0..n-1], n = m + 4, and c[d*n + i].  Returns n, or -1. */
+int fpk_parcur_open(const double *u0, const double *x0, int m, int idim, double *t0, double *c0)
+{
+    const int k = 3, k1 = 4;
+    if (m < 4 || idim < 1 || idim > 4) return -1;
+    int n = m + k1, nk1 = n - k1;
+    const double *u = u0 - 1, *x = x0 - 1;
+    double *t = t0 - 1, *c = c0 - 1;
+    for (int i = 1; i <= k1; ++i) {
+        t[i] = u[1];
+        t[nk1 + i] = u[m];
+    }
+    for (int l = 1, i = k + 2, j = k / 2 + 2; l <= m - k1; ++l) t[i++] = u[j++];
+    double(*a)[5] = calloc((size_t)nk1 + 2, sizeof *a);
+    double *z = calloc((size_t)idim * n + 2, sizeof *z);
+    for (int i = 1; i <= idim * n; ++i) c[i] = 0.0;
+    double h[8], xi[4];
+    int l = k1, jj = 0;
+    for (int it = 1; it <= m; ++it) {
+        double ui = u[it];
+        for (int d = 0; d < idim; ++d) xi[d] = x[++jj];
+        while (!(ui < t[l + 1] || l == nk1)) ++l;
+        fpbspl(t, k, ui, l, h);
+        int j = l - k1;
+        for (int i = 1; i <= k1; ++i) {
+            ++j;
+            double piv = h[i];
+            if (piv == 0.0) continue;
+            double co, si;
+            fpgivs(piv, &a[j][1], &co, &si);
+            for (int d = 0, j1 = j; d < idim; ++d, j1 += n) fprota(co, si, &xi[d], &z[j1]);
+            if (i == k1) break;
+            int i2 = 1;
+            for (int i1 = i + 1; i1 <= k1; ++i1) {
+                ++i2;
+                fprota(co, si, &h[i1], &a[j][i2]);
+            }
+        }
+    }
+    for (int d = 0; d < idim; ++d) { /* fpback */
+        double *zz = z + d * n, *cc = c + d * n;
+        cc[nk1] = zz[nk1] / a[nk1][1];
+        int i = nk1 - 1;
+        for (int j = 2; j <= nk1; ++j) {
+            double store = zz[i];
+            int i1 = j <= k ? j - 1 : k, mm = i;
+            for (int q = 1; q <= i1; ++q) {
+                ++mm;
+                store = store - cc[mm] * a[i][q + 1];
+            }
+            cc[i] = store / a[i][1];
+            --i;
+        }
+    }
+    free(a);
+    free(z);
+    return n;
+}

@@ -52,4 +52,30 @@ int fitcore_curvature(int N, const double* t, const double* w1x, const double* w
     return 0;
 }
 
+// general evaluation: derivative nu (0..2) of the spline (t [n], cx, cy [n - 4]) at x [m]
+int fitcore_splev(int n, const double* t, const double* cx, const double* cy, int nu, const double* x, int m,
+                  double* ox, double* oy)
+{
+    std::vector<double> w1x(n), w1y(n), w2x(n), w2y(n);
+    der_coeffs(t, n, cx, w1x.data(), w2x.data());
+    der_coeffs(t, n, cy, w1y.data(), w2y.data());
+    const double* kx = nu == 0 ? cx : nu == 1 ? w1x.data() : w2x.data();
+    const double* ky = nu == 0 ? cy : nu == 1 ? w1y.data() : w2y.data();
+    for (int i = 0; i < m; ++i) {
+        const int l = find_interval(t, n, x[i]);
+        ox[i] = splev_at(t, kx, nu, x[i], l);
+        oy[i] = splev_at(t, ky, nu, x[i], l);
+    }
+    return 0;
+}
+
+// open (not-a-knot) interpolating spline: u, px, py [m] -> t [m + 4], cx, cy [m]
+int fitcore_solve_open(int m, const double* u, const double* px, const double* py, double* t, double* cx, double* cy)
+{
+    if (m < 4) return -1;
+    std::vector<double> a((size_t)4 * m), z((size_t)2 * m);
+    solve_open(m, u, px, py, t, a.data(), z.data(), cx, cy);
+    return 0;
+}
+
 }  // extern "C"

@@ -124,6 +124,46 @@ def test_path_facade(golden):
     ev.close()
 
 
+def test_path_facade_fitpack_arithmetic(golden):
+    """Path in FITPACK arithmetic: `Path.spline` == splprep's tck, positions / derivatives-derived curvature ==
+    the reference's (splev), closed and open paths; the batched FITPACK-mode kernels build the same spline."""
+    from scipy.interpolate import splev, splprep
+
+    g = golden("buckmore_tbr18_bayes")
+    c = g["prof_controls"][0].copy()
+    s = g["prof_s"][0]
+    p = ltk.Path(c.copy(), True, spline="fitpack")
+    t, cc, k = p.spline
+    assert k == 3 and np.array_equal(t, g["prof_tck_t"][0])
+    assert np.array_equal(cc[0], g["prof_tck_cx"][0]) and np.array_equal(cc[1], g["prof_tck_cy"][0])
+    kk = p.curvature(s[:-1])
+    kb = g["prof_k_base"][0]
+    assert np.all(np.abs(kk - kb) <= 2 * np.spacing(np.maximum(kk, kb))) and (kk != kb).mean() <= 0.005
+    xy = p.position(s)
+    want = splev(s, (t, cc, 3))
+    assert np.array_equal(xy[0], want[0]) and np.array_equal(xy[1], want[1])
+    ev, _ = make("buckmore_tbr18_bayes", spline="fitpack")
+    assert np.array_equal(ev.profile(g["alphas"][0])["k"], kk)
+    ev.close()
+    # the default-mode facade still offers the tck (computed by the FITPACK kernel)
+    assert np.array_equal(ltk.Path(c.copy(), True).spline[0], t)
+    # open path: splprep(per=0) is the not-a-knot spline (path.py:25 with closed = False)
+    o = c[:, :30].copy()
+    po = ltk.Path(o, False)
+    (t0, c0, _k), _ = splprep(o, u=po.dists, k=3, s=0, per=0)
+    ts, cs, _ = po.spline
+    assert np.array_equal(ts, t0) and np.array_equal(cs[0], c0[0]) and np.array_equal(cs[1], c0[1])
+    u = np.linspace(0, po.length, 333)
+    d1, d2 = splev(u, (t0, c0, 3), der=1), splev(u, (t0, c0, 3), der=2)
+    kref = (d1[0] * d2[1] - d1[1] * d2[0]) / (d1[0] ** 2 + d1[1] ** 2) ** 1.5
+    ko = po.curvature(u, return_absolute_value=False)
+    assert np.all(np.abs(ko - kref) <= 3 * np.spacing(np.abs(kref)))
+    xo = po.position(u)
+    w = splev(u, (t0, c0, 3))
+    assert np.array_equal(xo[0], w[0]) and np.array_equal(xo[1], w[1])
+    assert abs(po.gamma2(u) - np.sum(kref ** 2)) <= 1e-12 * np.sum(kref ** 2)
+
+
 # ---- full BASELINE.json size ------------------------------------------------------------------------
 @pytest.mark.parametrize("veh", ["tbr18", "mx5"])
 def test_full_size_population_bit_exact_and_topk(veh):
@@ -242,6 +282,17 @@ def test_spline_mode_switch_and_ragged(buckmore):
     finally:
         ev.set_spline_mode("tridiagonal")
     assert np.array_equal(ev.lap_times(a), co.lap_times(a))
+
+
+@pytest.mark.parametrize("spline", ["tridiagonal", "fitpack"])
+def test_two_pass_k1b_bit_exact(monkeypatch, spline):
+    """The curvature kernel without the shared-memory tile (what dense sampling, ns > ~6,600, selects): forced here
+    at the default density so that a 16,384-candidate population checks it against the C oracle."""
+    monkeypatch.setenv("LTK_K1_STAGED", "0")
+    ev, co = make("buckmore_tbr18_bayes", spline=spline)
+    a = np.random.default_rng(12).uniform(0.0, 0.99, (16384, ev.n_alpha))
+    assert np.array_equal(ev.lap_times(a), co.lap_times(a))
+    ev.close()
 
 
 def make_oracle_only(name, spline):

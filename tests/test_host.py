@@ -72,8 +72,9 @@ def test_path_host_attributes_and_closure_quirk():
     # like splprep(per=1): the caller's last column now equals the first
     assert np.array_equal(c[:, -1], c[:, 0]) and not np.array_equal(before[:, -1], before[:, 0])
     assert p.controls is c
-    with pytest.raises(AttributeError):
-        p.spline
+    if not torch.cuda.is_available():  # Path.spline is computed by the CUDA FITPACK kernel: no CPU fallback
+        with pytest.raises(ltk.LtkUnavailable):
+            p.spline
 
 
 def test_abi_exports_every_declared_symbol():
@@ -195,6 +196,8 @@ def fitcore(tmp_path_factory):
     dp = ctypes.POINTER(ctypes.c_double)
     lib.fitcore_solve.argtypes = [ctypes.c_int] + [dp] * 10
     lib.fitcore_curvature.argtypes = [ctypes.c_int] + [dp] * 6 + [ctypes.c_int] + [dp] * 5
+    lib.fitcore_splev.argtypes = [ctypes.c_int, dp, dp, dp, ctypes.c_int, dp, ctypes.c_int, dp, dp]
+    lib.fitcore_solve_open.argtypes = [ctypes.c_int] + [dp] * 6
     return lib
 
 
@@ -253,3 +256,36 @@ def test_device_fitpack_arithmetic_equals_reference_and_oracle(fitcore, name):
         for key in ("dx", "dy", "ddx", "ddy"):
             assert np.array_equal(got[key], g["prof_" + key][i]), key
         assert np.array_equal(got["k"], co.profile(g["alphas"][i])["k"])
+
+
+def test_device_open_spline_and_general_evaluation_equal_scipy(fitcore):
+    """The Path facade's FITPACK kernel pieces on the host: the open (not-a-knot) solve == splprep(per=0), and the
+    general splev / splder evaluation (positions, first and second derivatives, end point and knots included)
+    == splev, bit for bit, for open and closed splines."""
+    from scipy.interpolate import splev, splprep
+
+    dp = ctypes.POINTER(ctypes.c_double)
+    p = lambda a: a.ctypes.data_as(dp)  # noqa: E731
+    rng = np.random.default_rng(31)
+    for trial in range(60):
+        per = trial % 2
+        m = int(rng.integers(6, 130))
+        th = np.sort(rng.uniform(0, 1.8 * np.pi, m))
+        r = rng.uniform(50, 120, m)
+        pts = np.array([r * np.cos(th), r * np.sin(th)])
+        if per:
+            pts[:, -1] = pts[:, 0]
+        u = np.append(0, np.cumsum(np.linalg.norm(np.diff(pts, axis=1), axis=0)))
+        (t, c, k), _ = splprep(pts.copy(), u=u, k=3, s=0, per=per)
+        if not per:
+            t2, cx, cy = np.zeros(m + 4), np.zeros(m), np.zeros(m)
+            assert fitcore.fitcore_solve_open(m, p(u), p(np.ascontiguousarray(pts[0])), p(np.ascontiguousarray(pts[1])),
+                                              p(t2), p(cx), p(cy)) == 0
+            assert np.array_equal(t, t2) and np.array_equal(c[0], cx) and np.array_equal(c[1], cy)
+        x = np.concatenate([np.linspace(0, u[-1], 150), u])
+        tt, cx, cy = np.ascontiguousarray(t), np.ascontiguousarray(c[0]), np.ascontiguousarray(c[1])
+        for nu in (0, 1, 2):
+            want = splev(x, (t, c, k), der=nu)
+            ox, oy = np.zeros(x.size), np.zeros(x.size)
+            fitcore.fitcore_splev(tt.size, p(tt), p(cx), p(cy), nu, p(x), x.size, p(ox), p(oy))
+            assert np.array_equal(ox, want[0]) and np.array_equal(oy, want[1]), (trial, nu)

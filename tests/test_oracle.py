@@ -134,6 +134,27 @@ def test_fitpack_port_equals_live_scipy():
                 assert np.array_equal(ys[d], c_oracle.fitpack_splder(t2, c2[d], nu, x)), (trial, nu, d)
 
 
+def test_fitpack_port_open_spline_equals_live_scipy():
+    """fppara (s = 0, per = 0: the not-a-knot interpolating spline of open paths) restated in C against SciPy."""
+    from scipy.interpolate import splev, splprep
+
+    rng = np.random.default_rng(12)
+    for trial in range(40):
+        m = int(rng.integers(4, 140))
+        th = np.sort(rng.uniform(0, 1.7 * np.pi, m))
+        r = rng.uniform(50, 120, m)
+        pts = np.array([r * np.cos(th), r * np.sin(th)])
+        u = np.append(0, np.cumsum(np.linalg.norm(np.diff(pts, axis=1), axis=0)))
+        (t, c, k), _ = splprep(pts.copy(), u=u, k=3, s=0, per=0)
+        t2, c2 = c_oracle.fitpack_spline_open(u, pts)
+        assert np.array_equal(t, t2) and np.array_equal(c[0], c2[0]) and np.array_equal(c[1], c2[1])
+        x = np.linspace(0, u[-1], 201)
+        for nu in (0, 1, 2):
+            ys = splev(x, (t, c, k), der=nu)
+            for d in range(2):
+                assert np.array_equal(ys[d], c_oracle.fitpack_splder(t2, c2[d], nu, x)), (trial, nu, d)
+
+
 @pytest.mark.parametrize("name", golden_cases())
 def test_fitpack_port_equals_reference_spline(name, golden):
     """Same check against what the unmodified reference held in Path.spline (tools/make_golden.py)."""
