@@ -354,7 +354,7 @@ bool pick_k1f(const ltk_ctx* ctx, K1FConfig* out)
     // measured order.  The shared-memory tile (staged) wins while four candidates' rows fit; beyond that
     // (ns > ~6,600) the two-pass variant at G = 4 does (profiles/README.md, ns = 10,001).  G = 1, 2 tiles are
     // only reachable through LTK_K1_G.
-    const int cand[8][3] = {{4, 256, 1}, {4, 128, 1}, {8, 256, 1}, {4, 256, 0}, {2, 128, 1}, {2, 64, 1}, {1, 256, 1}, {1, 128, 1}};
+    const int cand[8][3] = {{4, 256, 1}, {4, 128, 1}, {8, 256, 1}, {8, 512, 0}, {2, 128, 1}, {2, 64, 1}, {1, 256, 1}, {1, 128, 1}};
     for (int i = 0; i < 8; ++i) {
         int G = cand[i][0], T = cand[i][1], staged = cand[i][2];
         if (ctx->k1_g_override > 0 && G != ctx->k1_g_override) continue;
@@ -379,7 +379,7 @@ cudaError_t launch_k1f(const K1Args& a, const FitArgs& fa, size_t smem, cudaStre
 template <bool FIT>
 cudaError_t launch_k1f_cfg(const K1FConfig& c, const K1Args& a, const FitArgs& fa, cudaStream_t st)
 {
-    if (!c.staged) return launch_k1f<4, 256, 4, FIT, false>(a, fa, c.smem, st);
+    if (!c.staged) return launch_k1f<8, 512, 2, FIT, false>(a, fa, c.smem, st);
     if (c.G == 1 && c.threads == 256) return launch_k1f<1, 256, 2, FIT>(a, fa, c.smem, st);
     if (c.G == 1) return launch_k1f<1, 128, 4, FIT>(a, fa, c.smem, st);
     if (c.G == 2 && c.threads == 128) return launch_k1f<2, 128, 8, FIT>(a, fa, c.smem, st);

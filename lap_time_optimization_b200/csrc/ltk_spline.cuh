@@ -185,8 +185,9 @@ __global__ void __launch_bounds__(K1A_THREADS, 4) k1a_solve(K1Args a)
 // hand-off arrays are then K1a-F's knots t [N+7] and derivative coefficients wrk1 [N+2], wrk2 [N+1] per coordinate.
 // STAGED = false: two passes over the samples instead of the shared-memory tile -- the first finds the rotation,
 // the second recomputes the curvatures and writes them straight to their rotated rows.  Twice the arithmetic,
-// but the kernel keeps G = 4 and full occupancy when the tile would not fit (ns = 10,001: 8.0 ms with the tile at
-// G = 2 and one CTA per SM against 3.4 ms for the old two-pass kernel).
+// but full occupancy when the tile would not fit (ns = 10,001: 8.0 ms with the tile at G = 2 and one CTA per SM).
+// Run at G = 8: half-line (64-byte) row segments; at G = 4 the 32-byte segments of four CTAs reached DRAM as
+// partial lines (ncu: 0.56 GB of DRAM reads for a kernel that only writes).
 template <int G, int T, int MINB, bool FIT, bool STAGED>
 __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a, FitArgs fa)
 {
@@ -334,24 +335,26 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a, FitArgs fa)
     const double step = LEN[g] / (double)(a.ns - 1);
     // One flat loop per run of samples: every lane of the warp runs the same number of iterations (nested
     // per-interval loops diverge -- interval boundaries differ from lane to lane -- and ran at 19 of
-    // 32 lanes); the interval switch is an integer test that fires about once per 20 samples.
-    auto walk = [&](int q0, int q1, auto&& sink) {  // curvature at samples q0 .. q1-1 of candidate g
-        if (q0 >= q1) return;
-        int lo = 0, hi = N - 1;  // interval of sample q0: largest j with IB[j] <= q0
+    // 32 lanes); the interval switch is an integer test that fires about once per 20 samples, the wrap of the
+    // sample index (second pass of the two-pass variant: the lanes' rotations differ) at most once per run.
+    auto walk = [&](int qa, int count, auto&& sink) {  // samples qa, qa+1, ... (mod n) of candidate g
+        if (count <= 0) return;
+        int q = (qa >= n) ? qa - n : qa;
+        int lo = 0, hi = N - 1;  // interval of sample q: largest j with IB[j] <= q
         while (lo < hi) {
             const int mid = (lo + hi + 1) >> 1;
-            if (IB[mid * G + g] <= q0) lo = mid; else hi = mid - 1;
+            if (IB[mid * G + g] <= q) lo = mid; else hi = mid - 1;
         }
         int j = lo;
         Rec v = REC[j * G + g];
         int inext = IB[(j + 1) * G + g];
-        for (int i = q0; i < q1; ++i) {
-            while (i >= inext) {
+        for (int r = 0; r < count; ++r) {
+            while (q >= inext) {
                 ++j;
                 v = REC[j * G + g];
                 inext = IB[(j + 1) * G + g];
             }
-            const double s = (double)i * step;
+            const double s = (double)q * step;
             double k;
             if constexpr (FIT) {
                 double dx, dy, ddx, ddy;
@@ -366,14 +369,20 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a, FitArgs fa)
                 const double n2 = fma(dx, dx, dy * dy);
                 k = ddiv<false>(cross, n2 * dsqrt<false>(n2));
             }
-            sink(i, k);
+            sink(r, q, k);
+            if (!STAGED && ++q == n) {  // wrap: back to the first interval
+                q = 0; j = 0;
+                v = REC[g];
+                inext = IB[G + g];
+            }
+            if (STAGED) ++q;
         }
     };
     double best = -1.0;
     int bi = 0;
-    walk(i0, i1, [&](int i, double k) {
-        if constexpr (STAGED) KT[(size_t)i * G + g] = k;
-        if (k > best) { best = k; bi = i; }
+    walk(i0, i1 - i0, [&](int, int q, double k) {
+        if constexpr (STAGED) KT[(size_t)q * G + g] = k;
+        if (k > best) { best = k; bi = q; }
     });
     // first maximum of the curvature == a minimum of v_local (velocity.py:34).  Lanes l, l+G, l+2G, ...
     // hold consecutive chunks of one candidate: fold the upper lanes into the lower ones, lower chunk first
@@ -411,19 +420,13 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a, FitArgs fa)
                 if (dst32) dst32[(size_t)i * TILE] = (float)k;
             }
         } else {
-            // second pass: this thread's rows i0 .. i1-1 are the samples i0+q0 .. i1+q0-1 (mod n), one wrap at most;
-            // the G candidates of a row are written by adjacent lanes (one 32-byte sector at G = 4)
-            auto put = [&](int row0, int qa, int qb) {
-                walk(qa, qb, [&](int q, double k) {
-                    const size_t r = (size_t)(row0 + (q - qa)) * TILE;
-                    dst[r] = k;
-                    if (dst32) dst32[r] = (float)k;
-                });
-            };
-            const int qa = i0 + q0, qb = i1 + q0;
-            if (qa >= n) put(i0, qa - n, qb - n);
-            else if (qb <= n) put(i0, qa, qb);
-            else { put(i0, qa, n); put(i0 + (n - qa), 0, qb - n); }
+            // second pass: this thread's rows i0 .. i1-1 are the samples i0+q0 .. i1+q0-1 (mod n); the G
+            // candidates of a row are written by adjacent lanes (64 contiguous bytes at G = 8)
+            walk(i0 + q0, i1 - i0, [&](int r, int, double k) {
+                const size_t row = (size_t)(i0 + r) * TILE;
+                dst[row] = k;
+                if (dst32) dst32[row] = (float)k;
+            });
         }
     }
 }
