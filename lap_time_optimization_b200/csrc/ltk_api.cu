@@ -385,7 +385,13 @@ cudaError_t launch_k1f_cfg(const K1FConfig& c, const K1Args& a, const FitArgs& f
     if (c.G == 2 && c.threads == 128) return launch_k1f<2, 128, 8, FIT>(a, fa, c.smem, st);
     if (c.G == 2) return launch_k1f<2, 64, 12, FIT>(a, fa, c.smem, st);
     if (c.G == 4 && c.threads == 128) return launch_k1f<4, 128, 5, FIT>(a, fa, c.smem, st);
-    if (c.G == 4) return launch_k1f<4, 256, 4, FIT>(a, fa, c.smem, st);
+    if (c.G == 4) {
+        // A/B knob (FITPACK mode: the 160-byte interval record spills at 64 registers)
+        static const int minb = getenv("LTK_K1B_MINB") ? atoi(getenv("LTK_K1B_MINB")) : 0;
+        if (minb == 3) return launch_k1f<4, 256, 3, FIT>(a, fa, c.smem, st);
+        if (minb == 2) return launch_k1f<4, 256, 2, FIT>(a, fa, c.smem, st);
+        return launch_k1f<4, 256, 4, FIT>(a, fa, c.smem, st);
+    }
     return launch_k1f<8, 256, 2, FIT>(a, fa, c.smem, st);
 }
 

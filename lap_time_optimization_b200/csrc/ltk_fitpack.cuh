@@ -23,6 +23,36 @@ __host__ __device__ inline size_t fit_region_doubles(int N)
     return (size_t)(N + 7) + 7 * (size_t)N + 2 * (size_t)(N + 3) + 2 * (size_t)(N + 2) + 2 * (size_t)(N + 1);
 }
 
+// control point j of candidate b in two steps (fit::solve): loads, then track.py:87,:94 / the caller's points
+struct K1Points {
+    struct Raw { double al, lx, ly, dx, dy; };
+    const K1Args& a;
+    long long b;
+    __device__ __forceinline__ void fetch(int j, Raw& r) const
+    {
+        if (a.mode == 0) {
+            r.al = a.alphas[b * a.N + j];
+            r.lx = a.left[j]; r.dx = a.diff[j];
+            r.ly = a.left[a.N + j]; r.dy = a.diff[a.N + j];
+        } else {
+            r.lx = a.xy[(b * 2 + 0) * a.m + j];
+            r.ly = a.xy[(b * 2 + 1) * a.m + j];
+            r.al = r.dx = r.dy = 0.0;
+        }
+    }
+    __device__ __forceinline__ void finish(const Raw& r, double& x, double& y) const
+    {
+        if (a.mode == 0) { x = r.lx + r.al * r.dx; y = r.ly + r.al * r.dy; }
+        else { x = r.lx; y = r.ly; }
+    }
+};
+struct SmemPoints {  // the one-path facade kernel: points already in shared memory
+    struct Raw { double x, y; };
+    const double *px, *py;
+    __device__ __forceinline__ void fetch(int j, Raw& r) const { r.x = px[j]; r.y = py[j]; }
+    __device__ __forceinline__ void finish(const Raw& r, double& x, double& y) const { x = r.x; y = r.y; }
+};
+
 __global__ void __launch_bounds__(K1AF_THREADS) k1a_fitpack(K1Args a, FitArgs f)
 {
     extern __shared__ __align__(16) double smf[];
@@ -30,20 +60,26 @@ __global__ void __launch_bounds__(K1AF_THREADS) k1a_fitpack(K1Args a, FitArgs f)
     double* TK = smf;  // [N + 7][32]; row l-1 holds FITPACK's t(l)
     const long long b = (long long)blockIdx.x * 32 + lane;
     const long long bb = (b < a.B) ? b : a.B - 1;  // padding lanes repeat the last candidate
-    auto point = [&](int j, double& x, double& y) { control_point(a, bb, j, x, y); };  // track.py:87,:94
-    // knots: np.cumsum of the chord lengths of the closed polygon (path.py:13-14); t(4 + j) = u_j
+    const K1Points pts{a, bb};
+    // knots: np.cumsum of the chord lengths of the closed polygon (path.py:13-14); t(4 + j) = u_j.
+    // The loads of point j+2 are in flight while the chord j -> j+1 is measured.
     {
-        double acc = 0.0, x0, y0;
-        point(0, x0, y0);
+        double acc = 0.0, x0, y0, xp, yp, xn, yn;
+        K1Points::Raw r0, r1, r2;
+        pts.fetch(0, r0);
+        pts.fetch(1, r1);
+        pts.finish(r0, x0, y0);
         TK[3 * 32 + lane] = 0.0;
-        double xp = x0, yp = y0;
+        xp = x0; yp = y0;
         for (int j = 0; j < N; ++j) {
-            double xn = x0, yn = y0;
-            if (j + 1 < N) point(j + 1, xn, yn);
+            if (j + 2 < N) pts.fetch(j + 2, r2);
+            if (j + 1 < N) pts.finish(r1, xn, yn);
+            else { xn = x0; yn = y0; }
             const double ex = xn - xp, ey = yn - yp;
             acc = acc + dsqrt<false>(ex * ex + ey * ey);
             TK[(j + 4) * 32 + lane] = acc;
             xp = xn; yp = yn;
+            r1 = r2;
         }
     }
     fit::Io io;
@@ -51,7 +87,7 @@ __global__ void __launch_bounds__(K1AF_THREADS) k1a_fitpack(K1Args a, FitArgs f)
     io.rows = f.rows + b; io.sr = (long)a.Bp;
     io.cx = f.cx + b; io.cy = f.cy + b; io.sc = (long)a.Bp;
     io.w1x = f.w1x + b; io.w1y = f.w1y + b; io.w2x = f.w2x + b; io.w2y = f.w2y + b; io.sw = (long)a.Bp;
-    fit::solve(N, io, point);
+    fit::solve(N, io, pts);
     for (int l = 0; l < N + 7; ++l) f.t[(size_t)l * a.Bp + b] = TK[l * 32 + lane];
 }
 
@@ -104,7 +140,7 @@ __global__ void __launch_bounds__(256) path_fit_kernel(PathFitArgs a)
             io.rows = SCR; io.sr = 1;
             io.cx = CX; io.cy = CY; io.sc = 1;
             io.w1x = W1X; io.w1y = W1Y; io.w2x = W2X; io.w2y = W2Y; io.sw = 1;
-            fit::solve(N, io, [&](int j, double& x, double& y) { x = PX[j]; y = PY[j]; });
+            fit::solve(N, io, SmemPoints{PX, PY});
         } else {
             double* A = SCR;         // [4 m]
             double* Z = A + 4 * m;   // [2 m]

@@ -45,6 +45,14 @@ LTK_HD double fdiv(double a, double b)
     return a / b;
 #endif
 }
+LTK_HD void prefetch(const double* p)  // into L1, several rows ahead of a dependent loop (no-op on the host)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
 LTK_HD double fsqrt(double x)
 {
 #if defined(__CUDA_ARCH__)
@@ -258,17 +266,23 @@ struct Io {
         LTK_R(j, 4) = (W).e2; LTK_R(j, 5) = (W).zx; LTK_R(j, 6) = (W).zy;                                      \
     } while (0)
 
-// The whole solve for one candidate with N >= 5 unique control points.  point(j, x, y) yields control point j
-// (0-based, unique points only).
+// The whole solve for one candidate with N >= 5 unique control points.  Control point j (0-based, unique points
+// only) comes in two steps so that its loads can be issued a whole data row before the values are needed:
+// pts.fetch(j, raw) only loads, pts.finish(raw, x, y) does the arithmetic.
 //
 // Schedule of the forward pass.  Per data row `it` FITPACK performs three band rotations (into rows it, it+1,
 // it+2) and, in our fused order, the two wrapping rows A and B are rotated through row `it` once it is final.
 // The third band rotation always meets a fresh row (diagonal 0): fpgivs then gives c = 0, s = +-1 exactly, so it is
 // a copy.  The remaining four form two dependency chains per row -- band1(it) -> band2(it) -> band1(it+1) and
 // band1(it) -> A(it) -> B(it) -- which are issued as the pairs  band1(it) || B(it-1)  and  band2(it) || A(it).
-template <class PointFn>
-LTK_HD void solve(int N, const Io& io, PointFn point)
+template <class Points>
+LTK_HD void solve(int N, const Io& io, Points pts)
 {
+    auto point = [&](int j, double& x, double& y) {
+        typename Points::Raw raw;
+        pts.fetch(j, raw);
+        pts.finish(raw, x, y);
+    };
     const int n10 = N - 2;
     // periodic knot extension: t(4 - j) = t(N + 4 - j) - per, t(N + 4 + j) = t(4 + j) + per
     const double per = LTK_T(N + 4) - LTK_T(4);
@@ -297,9 +311,11 @@ LTK_HD void solve(int N, const Io& io, PointFn point)
     point(0, xn, yn);
     for (int it = 1; it <= n10; ++it) {
         double h1 = hn1, h2 = hn2, h3 = hn3, x = xn, y = yn, c, s, cw, sw;
-        // operands of data row it+1 (row n10+1 = A exists as well: the values are simply not used after the loop)
+        // operands of data row it+1 (row n10+1 = A exists as well: the values are simply not used after the loop);
+        // the control point's loads are issued here and consumed at the end of the iteration
         tm2 = tm1; tm1 = t0; t0 = tp1; tp1 = tp2; tp2 = LTK_T(it + 6);
-        point(it, xn, yn);
+        typename Points::Raw raw;
+        pts.fetch(it, raw);
         BsplMid mid;
         // ---- band1(it) || B(it-1)  [+ first half of the next B-spline row]
         if (it >= 2 && h1 != 0.0 && B.h1[0] != 0.0) {
@@ -352,6 +368,7 @@ LTK_HD void solve(int N, const Io& io, PointFn point)
         }
         Wp = W0; W0 = W1; W1 = W2;
         W2.a = W2.b = W2.c = W2.e1 = W2.e2 = W2.zx = W2.zy = 0.0;
+        pts.finish(raw, xn, yn);
     }
     wrap_rotate(B, Wp, n10, n10);
     LTK_STORE_ROW(n10, Wp);
@@ -368,9 +385,14 @@ LTK_HD void solve(int N, const Io& io, PointFn point)
     // the next row is fetched before the current one's divisions: the loads do not wait for the chain
     double ra = LTK_R(n10, 0), rb = LTK_R(n10, 1), rc = LTK_R(n10, 2), re1 = LTK_R(n10, 3), re2 = LTK_R(n10, 4),
            rzx = LTK_R(n10, 5), rzy = LTK_R(n10, 6);
+    constexpr int AHEAD = 4;  // rows fetched into L1 ahead of the register look-ahead
+    for (int i = n10 - 1; i >= 1 && i >= n10 - AHEAD; --i)
+        for (int e = 0; e < 7; ++e) prefetch(&LTK_R(i, e));
     for (int i = n10; i >= 1; --i) {
         const double a = ra, b = rb, cc = rc, e1 = re1, e2 = re2;
         double sx = rzx, sy = rzy;
+        if (i - 1 - AHEAD >= 1)
+            for (int e = 0; e < 7; ++e) prefetch(&LTK_R(i - 1 - AHEAD, e));
         if (i > 1) {
             ra = LTK_R(i - 1, 0); rb = LTK_R(i - 1, 1); rc = LTK_R(i - 1, 2); re1 = LTK_R(i - 1, 3);
             re2 = LTK_R(i - 1, 4); rzx = LTK_R(i - 1, 5); rzy = LTK_R(i - 1, 6);
@@ -385,10 +407,12 @@ LTK_HD void solve(int N, const Io& io, PointFn point)
     }
     for (int q = 1; q <= 3; ++q) { LTK_CX(N + q) = LTK_CX(q); LTK_CY(N + q) = LTK_CY(q); }
     // splder: wrk1(i) = 3 (c(i+1) - c(i)) / (t(i+4) - t(i+1)),  wrk2(i) = 2 (wrk1(i+1) - wrk1(i)) / (t(i+4) - t(i+2))
+    for (int i = 3; i <= 2 + AHEAD; ++i) { prefetch(&LTK_CX(i)); prefetch(&LTK_CY(i)); }
     double px_ = LTK_CX(1), py_ = LTK_CY(1), w1px = 0, w1py = 0;
     double nx = LTK_CX(2), ny = LTK_CY(2);
     for (int i = 1; i <= N + 2; ++i) {
         const double cx1 = nx, cy1 = ny;
+        if (i + 2 + AHEAD <= N + 3) { prefetch(&LTK_CX(i + 2 + AHEAD)); prefetch(&LTK_CY(i + 2 + AHEAD)); }
         if (i <= N + 1) { nx = LTK_CX(i + 2); ny = LTK_CY(i + 2); }  // fetched one iteration ahead
         const double fac = LTK_T(i + 4) - LTK_T(i + 1);
         double w1x, w1y;

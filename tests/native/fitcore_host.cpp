@@ -27,7 +27,13 @@ int fitcore_solve(int N, const double* px, const double* py, const double* u, do
     io.rows = rows.data(); io.sr = 1;
     io.cx = cx; io.cy = cy; io.sc = 1;
     io.w1x = w1x; io.w1y = w1y; io.w2x = w2x; io.w2y = w2y; io.sw = 1;
-    solve(N, io, [&](int j, double& x, double& y) { x = px[j]; y = py[j]; });
+    struct Points {
+        struct Raw { double x, y; };
+        const double *px, *py;
+        void fetch(int j, Raw& r) const { r.x = px[j]; r.y = py[j]; }
+        void finish(const Raw& r, double& x, double& y) const { x = r.x; y = r.y; }
+    } pts{px, py};
+    solve(N, io, pts);
     return 0;
 }
 
