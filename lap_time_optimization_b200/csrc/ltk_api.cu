@@ -271,14 +271,10 @@ FitArgs fit_args(const ltk_ctx* ctx, char* ws, const WsLayout& w)
     FitArgs f;
     const size_t Bp = (size_t)w.Bp, N = (size_t)ctx->N;
     double* p = reinterpret_cast<double*>(ws + w.fit_off);
-    f.t = p; p += (N + 7) * Bp;
+    f.hand = p; p += (5 * N + 13) * Bp;  // first: the packed blocks stay 16-byte aligned (bulk copy)
     f.rows = p; p += 7 * N * Bp;
     f.cx = p; p += (N + 3) * Bp;
-    f.cy = p; p += (N + 3) * Bp;
-    f.w1x = p; p += (N + 2) * Bp;
-    f.w1y = p; p += (N + 2) * Bp;
-    f.w2x = p; p += (N + 1) * Bp;
-    f.w2y = p;
+    f.cy = p;
     return f;
 }
 
@@ -386,10 +382,13 @@ cudaError_t launch_k1f_cfg(const K1FConfig& c, const K1Args& a, const FitArgs& f
     if (c.G == 2) return launch_k1f<2, 64, 12, FIT>(a, fa, c.smem, st);
     if (c.G == 4 && c.threads == 128) return launch_k1f<4, 128, 5, FIT>(a, fa, c.smem, st);
     if (c.G == 4) {
-        // A/B knob (FITPACK mode: the 160-byte interval record spills at 64 registers)
+        // CTAs per SM: 4 (64 registers) for the tridiagonal mode; the FITPACK mode's 160-byte interval record spills
+        // there and runs faster at 3 (80 registers): 0.51 -> 0.41 ms; the tridiagonal mode loses (0.283 -> 0.306).
+        // LTK_K1B_MINB overrides (A/B).
         static const int minb = getenv("LTK_K1B_MINB") ? atoi(getenv("LTK_K1B_MINB")) : 0;
-        if (minb == 3) return launch_k1f<4, 256, 3, FIT>(a, fa, c.smem, st);
-        if (minb == 2) return launch_k1f<4, 256, 2, FIT>(a, fa, c.smem, st);
+        const int m = minb ? minb : (FIT ? 3 : 4);
+        if (m == 3) return launch_k1f<4, 256, 3, FIT>(a, fa, c.smem, st);
+        if (m == 2) return launch_k1f<4, 256, 2, FIT>(a, fa, c.smem, st);
         return launch_k1f<4, 256, 4, FIT>(a, fa, c.smem, st);
     }
     return launch_k1f<8, 256, 2, FIT>(a, fa, c.smem, st);
@@ -460,6 +459,7 @@ int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m
     a.mx = reinterpret_cast<double*>(ws + w.mx_off);
     a.my = reinterpret_cast<double*>(ws + w.my_off);
     a.knots = reinterpret_cast<double*>(ws + w.knots_off);
+    a.hand = a.mx;  // (3 N + 1) Bp doubles: the packed hand-off of the k1a_solve / k1b_samples pair
     auto trace_open = [&](int kind, cudaStream_t s_) {
         if (ctx->trace_ev && ctx->trace_n < ctx->trace_cap) {
             ctx->trace_kind[ctx->trace_n] = kind;

@@ -86,9 +86,12 @@ __global__ void __launch_bounds__(K1AF_THREADS) k1a_fitpack(K1Args a, FitArgs f)
     io.t = TK + lane; io.st = 32;
     io.rows = f.rows + b; io.sr = (long)a.Bp;
     io.cx = f.cx + b; io.cy = f.cy + b; io.sc = (long)a.Bp;
-    io.w1x = f.w1x + b; io.w1y = f.w1y + b; io.w2x = f.w2x + b; io.w2y = f.w2y + b; io.sw = (long)a.Bp;
+    const int hrows = 5 * N + 13;
+    double* hand = f.hand + hand_index(b, hrows, 0);
+    io.w1x = hand + (size_t)(N + 7) * HAND_G; io.w1y = io.w1x + (size_t)(N + 2) * HAND_G;
+    io.w2x = io.w1y + (size_t)(N + 2) * HAND_G; io.w2y = io.w2x + (size_t)(N + 1) * HAND_G; io.sw = HAND_G;
     fit::solve(N, io, pts);
-    for (int l = 0; l < N + 7; ++l) f.t[(size_t)l * a.Bp + b] = TK[l * 32 + lane];
+    for (int l = 0; l < N + 7; ++l) hand[(size_t)l * HAND_G] = TK[l * 32 + lane];
 }
 
 // ------------------------------------------------------------------------------------------------

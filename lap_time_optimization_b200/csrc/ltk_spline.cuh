@@ -89,13 +89,13 @@ __global__ void __launch_bounds__(K1A_THREADS, 4) k1a_solve(K1Args a)
     }
     __syncthreads();
     if (rhs == 0) {  // knots: np.cumsum order (path.py:14); interval widths are knot differences
-        const long long b = b0 + lane;
+        double* kn = a.hand + hand_index(b0 + lane, 3 * N + 1, 0);
         double acc = 0.0;
-        a.knots[b] = 0.0;
+        kn[0] = 0.0;
         for (int j = 0; j < N; ++j) {
             const double prev = acc;
             acc = acc + S1(H, j);
-            a.knots[(size_t)(j + 1) * a.Bp + b] = acc;
+            kn[(size_t)(j + 1) * HAND_G] = acc;
             S1(H, j) = acc - prev;
         }
     }
@@ -167,13 +167,13 @@ __global__ void __launch_bounds__(K1A_THREADS, 4) k1a_solve(K1Args a)
     if (rhs < 2) {  // Sherman-Morrison correction, store M_x / M_y
         const long long b = b0 + lane;
         const double* R = (rhs == 0) ? RX : RY;
-        double* out = (rhs == 0) ? a.mx : a.my;
+        double* out = a.hand + hand_index(b, 3 * N + 1, (rhs == 0) ? N + 1 : 2 * N + 1);
         const double hl = S1(H, N - 1);
         const double gamma = -(2.0 * (hl + S1(H, 0)));
         const double vN = hl / gamma;
         const double denom = 1.0 + (S1(RZ, 0) + vN * S1(RZ, N - 1));
         const double fs = (S1(R, 0) + vN * S1(R, N - 1)) / denom;
-        for (int j = 0; j < N; ++j) out[(size_t)j * a.Bp + b] = S1(R, j) - fs * S1(RZ, j);
+        for (int j = 0; j < N; ++j) out[(size_t)j * HAND_G] = S1(R, j) - fs * S1(RZ, j);
     }
 #undef S1
 }
@@ -193,6 +193,7 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a, FitArgs fa)
 {
     static_assert(32 % G == 0 && T % 32 == 0, "lanes split evenly over the candidates of a CTA");
     extern __shared__ __align__(16) unsigned char smraw[];
+    __shared__ __align__(8) unsigned long long mbar;  // completion of the hand-off bulk copy
     const int N = a.N, n = a.ns - 1, NG = N * G;
     constexpr int NW = T / 32, CPT = T / G;
     using Rec = typename std::conditional<FIT, fit::FitInterval, Interval>::type;
@@ -222,15 +223,26 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a, FitArgs fa)
     const long long b0 = (long long)blockIdx.x * G;
 
     if constexpr (FIT) {
-        // ---- L (FITPACK mode): everything comes from K1a-F, candidate-minor rows of G consecutive doubles ----
-        for (int idx = tid; idx < (N + 7) * G; idx += T) {
-            const int j = idx / G, g = idx - j * G;
-            const size_t src = (size_t)j * a.Bp + b0 + g;
-            TK[idx] = fa.t[src];
-            if (j < N + 2) { W1X[idx] = fa.w1x[src]; W1Y[idx] = fa.w1y[src]; }
-            if (j < N + 1) { W2X[idx] = fa.w2x[src]; W2Y[idx] = fa.w2y[src]; }
+        // ---- L (FITPACK mode): everything comes from K1a-F: one bulk copy of the group's packed block (G = 4),
+        //      which has exactly the layout of the scratch arrays TK | W1X | W1Y | W2X | W2Y ----------------------
+        constexpr int ROWS_PER = 5;  // 5 N + 13 rows
+        const int rows = ROWS_PER * N + 13;
+        if constexpr (G == HAND_G) {
+            const unsigned bytes = (unsigned)rows * HAND_G * sizeof(double);
+            if (tid == 0) mbar_init(&mbar, 1);
+            __syncthreads();
+            if (tid == 0) {
+                mbar_expect_tx(&mbar, bytes);
+                bulk_g2s(TK, fa.hand + (size_t)blockIdx.x * rows * HAND_G, bytes, &mbar);
+            }
+            mbar_wait(&mbar, 0);
+        } else {
+            for (int idx = tid; idx < rows * G; idx += T) {
+                const int r = idx / G, g = idx - r * G;
+                TK[idx] = fa.hand[hand_index(b0 + g, rows, r)];
+            }
+            __syncthreads();
         }
-        __syncthreads();
         if (tid < G) LEN[tid] = U[NG + tid];
         __syncthreads();
         // ---- C (FITPACK mode): per-interval record (splder / fpbspl operands) and first sample index ---------
@@ -263,16 +275,19 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a, FitArgs fa)
         __syncthreads();
     } else {
 
-        // ---- L: control points from the alphas; knots and second derivatives from K1a.  The hand-off loads of the
-        //      first round are issued before the control-point loads are consumed, so the two latencies overlap ----
-        double u_first = 0.0, rx_first = 0.0, ry_first = 0.0, len_first = 0.0;
-        const bool first_row = tid < NG + G, first_m = tid < NG;
-        if (first_row) u_first = a.knots[(size_t)(tid / G) * a.Bp + b0 + (tid % G)];
-        if (first_m) {
-            rx_first = a.mx[(size_t)(tid / G) * a.Bp + b0 + (tid % G)];
-            ry_first = a.my[(size_t)(tid / G) * a.Bp + b0 + (tid % G)];
+        // ---- L: control points from the alphas; knots and second derivatives from K1a: one bulk copy of the
+        //      group's packed block (G = 4), whose layout is that of the scratch arrays U | RX | RY; it is in flight
+        //      while the control points are computed ----------------------------------------------------------
+        const int rows = 3 * N + 1;
+        if constexpr (G == HAND_G) {
+            if (tid == 0) mbar_init(&mbar, 1);
+            __syncthreads();
+            if (tid == 0) {
+                const unsigned bytes = (unsigned)rows * HAND_G * sizeof(double);
+                mbar_expect_tx(&mbar, bytes);
+                bulk_g2s(U, a.hand + (size_t)blockIdx.x * rows * HAND_G, bytes, &mbar);
+            }
         }
-        if (tid < G) len_first = a.knots[(size_t)N * a.Bp + b0 + tid];
         {   // T / G threads per candidate, j fastest: a candidate's alpha row is contiguous (no division by N)
             const int g = tid / CPT;
             long long b = b0 + g;
@@ -284,17 +299,16 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a, FitArgs fa)
                 PY[j * G + g] = y;
             }
         }
-        if (first_row) U[tid] = u_first;
-        if (first_m) { RX[tid] = rx_first; RY[tid] = ry_first; }
-        for (int idx = tid + T; idx < NG + G; idx += T) {
-            const int j = idx / G, g = idx - j * G;
-            U[idx] = a.knots[(size_t)j * a.Bp + b0 + g];
-            if (j < N) {
-                RX[idx] = a.mx[(size_t)j * a.Bp + b0 + g];
-                RY[idx] = a.my[(size_t)j * a.Bp + b0 + g];
+        if constexpr (G == HAND_G) {
+            mbar_wait(&mbar, 0);
+        } else {
+            for (int idx = tid; idx < rows * G; idx += T) {
+                const int r = idx / G, g = idx - r * G;
+                U[idx] = a.hand[hand_index(b0 + g, rows, r)];
             }
+            __syncthreads();
         }
-        if (tid < G) LEN[tid] = len_first;
+        if (tid < G) LEN[tid] = U[NG + tid];
         __syncthreads();
         // ---- C: per-interval coefficients  S'(t) = c1 + t (c2 + t h),  S''(t) = c2 + c3 t,  h = c3/2, and the
         //      first sample index of every interval: IB[j] = min{ i : fl(i*step) >= U[j] } ------------------
@@ -412,12 +426,26 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a, FitArgs fa)
         double* dst = a.kap + tile_base(b0 + g, n);
         float* dst32 = a.kap32 ? a.kap32 + tile_base(b0 + g, n) : nullptr;
         if constexpr (STAGED) {
-            for (int i = c; i < n; i += CPT) {
-                int q = i + q0;
-                q = (q >= n) ? q - n : q;
-                const double k = KT[(size_t)q * G + g];
-                dst[(size_t)i * TILE] = k;
-                if (dst32) dst32[(size_t)i * TILE] = (float)k;
+            if (G % 2 == 0 && !dst32) {
+                // two candidates per thread and row: one 16-byte store instead of two 8-byte ones, and half the
+                // index arithmetic (the write-out was 19 instructions per sample against 58 for its curvature)
+                const int gp = 2 * (tid % (G / 2)), cp = tid / (G / 2);
+                const int qa = ROT[gp], qb = ROT[gp + 1];
+                double2* d2 = reinterpret_cast<double2*>(a.kap + tile_base(b0 + gp, n));
+                for (int i = cp; i < n; i += 2 * CPT) {
+                    int ia = i + qa, ib = i + qb;
+                    ia = (ia >= n) ? ia - n : ia;
+                    ib = (ib >= n) ? ib - n : ib;
+                    d2[(size_t)i * (TILE / 2)] = make_double2(KT[(size_t)ia * G + gp], KT[(size_t)ib * G + gp + 1]);
+                }
+            } else {
+                for (int i = c; i < n; i += CPT) {
+                    int q = i + q0;
+                    q = (q >= n) ? q - n : q;
+                    const double k = KT[(size_t)q * G + g];
+                    dst[(size_t)i * TILE] = k;
+                    if (dst32) dst32[(size_t)i * TILE] = (float)k;
+                }
             }
         } else {
             // second pass: this thread's rows i0 .. i1-1 are the samples i0+q0 .. i1+q0-1 (mod n); the G
