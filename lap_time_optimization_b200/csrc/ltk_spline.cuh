@@ -426,7 +426,8 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a, FitArgs fa)
         double* dst = a.kap + tile_base(b0 + g, n);
         float* dst32 = a.kap32 ? a.kap32 + tile_base(b0 + g, n) : nullptr;
         if constexpr (STAGED) {
-            if (G % 2 == 0 && !dst32) {
+            bool done = false;
+            if constexpr (G % 2 == 0) if (!dst32) {
                 // two candidates per thread and row: one 16-byte store instead of two 8-byte ones, and half the
                 // index arithmetic (the write-out was 19 instructions per sample against 58 for its curvature)
                 const int gp = 2 * (tid % (G / 2)), cp = tid / (G / 2);
@@ -438,7 +439,9 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a, FitArgs fa)
                     ib = (ib >= n) ? ib - n : ib;
                     d2[(size_t)i * (TILE / 2)] = make_double2(KT[(size_t)ia * G + gp], KT[(size_t)ib * G + gp + 1]);
                 }
-            } else {
+                done = true;
+            }
+            if (!done) {
                 for (int i = c; i < n; i += CPT) {
                     int q = i + q0;
                     q = (q >= n) ? q - n : q;
