@@ -426,29 +426,12 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a, FitArgs fa)
         double* dst = a.kap + tile_base(b0 + g, n);
         float* dst32 = a.kap32 ? a.kap32 + tile_base(b0 + g, n) : nullptr;
         if constexpr (STAGED) {
-            bool done = false;
-            if constexpr (G % 2 == 0) if (!dst32) {
-                // two candidates per thread and row: one 16-byte store instead of two 8-byte ones, and half the
-                // index arithmetic (the write-out was 19 instructions per sample against 58 for its curvature)
-                const int gp = 2 * (tid % (G / 2)), cp = tid / (G / 2);
-                const int qa = ROT[gp], qb = ROT[gp + 1];
-                double2* d2 = reinterpret_cast<double2*>(a.kap + tile_base(b0 + gp, n));
-                for (int i = cp; i < n; i += 2 * CPT) {
-                    int ia = i + qa, ib = i + qb;
-                    ia = (ia >= n) ? ia - n : ia;
-                    ib = (ib >= n) ? ib - n : ib;
-                    d2[(size_t)i * (TILE / 2)] = make_double2(KT[(size_t)ia * G + gp], KT[(size_t)ib * G + gp + 1]);
-                }
-                done = true;
-            }
-            if (!done) {
-                for (int i = c; i < n; i += CPT) {
-                    int q = i + q0;
-                    q = (q >= n) ? q - n : q;
-                    const double k = KT[(size_t)q * G + g];
-                    dst[(size_t)i * TILE] = k;
-                    if (dst32) dst32[(size_t)i * TILE] = (float)k;
-                }
+            for (int i = c; i < n; i += CPT) {
+                int q = i + q0;
+                q = (q >= n) ? q - n : q;
+                const double k = KT[(size_t)q * G + g];
+                dst[(size_t)i * TILE] = k;
+                if (dst32) dst32[(size_t)i * TILE] = (float)k;
             }
         } else {
             // second pass: this thread's rows i0 .. i1-1 are the samples i0+q0 .. i1+q0-1 (mod n); the G
