@@ -362,12 +362,12 @@ bool pick_k1f(const ltk_ctx* ctx, K1FConfig* out)
     return false;
 }
 
-template <int G, int T, int MINB, bool FIT, bool STAGED = true>
+template <int G, int T, int MINB, bool FIT, bool STAGED = true, bool F32K = false>
 cudaError_t launch_k1f(const K1Args& a, const FitArgs& fa, size_t smem, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(k1b_samples<G, T, MINB, FIT, STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k1b_samples<G, T, MINB, FIT, STAGED, F32K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k1b_samples<G, T, MINB, FIT, STAGED><<<(unsigned)(a.Bp / G), T, smem, st>>>(a, fa);
+    k1b_samples<G, T, MINB, FIT, STAGED, F32K><<<(unsigned)(a.Bp / G), T, smem, st>>>(a, fa);
     g_launches.fetch_add(1);
     return cudaGetLastError();
 }
@@ -387,6 +387,11 @@ cudaError_t launch_k1f_cfg(const K1FConfig& c, const K1Args& a, const FitArgs& f
         // LTK_K1B_MINB overrides (A/B).
         static const int minb = getenv("LTK_K1B_MINB") ? atoi(getenv("LTK_K1B_MINB")) : 0;
         const int m = minb ? minb : (FIT ? 3 : 4);
+        if constexpr (!FIT) {
+            // fp32 variant: curvature evaluated in fp32 when only the fp32 copy is wanted (LTK_K1B_F32=0: fp64 + copy)
+            static const bool f32k = !(getenv("LTK_K1B_F32") && atoi(getenv("LTK_K1B_F32")) == 0);
+            if (a.kap32 && f32k) return launch_k1f<4, 256, 4, false, true, true>(a, fa, c.smem, st);
+        }
         if (m == 3) return launch_k1f<4, 256, 3, FIT>(a, fa, c.smem, st);
         if (m == 2) return launch_k1f<4, 256, 2, FIT>(a, fa, c.smem, st);
         return launch_k1f<4, 256, 4, FIT>(a, fa, c.smem, st);

@@ -188,9 +188,13 @@ __global__ void __launch_bounds__(K1A_THREADS, 4) k1a_solve(K1Args a)
 // but full occupancy when the tile would not fit (ns = 10,001: 8.0 ms with the tile at G = 2 and one CTA per SM).
 // Run at G = 8: half-line (64-byte) row segments; at G = 4 the 32-byte segments of four CTAs reached DRAM as
 // partial lines (ncu: 0.56 GB of DRAM reads for a kernel that only writes).
-template <int G, int T, int MINB, bool FIT, bool STAGED>
+// F32K = true (optional fp32 variant, ltk_set_sweep_precision(ctx, 32)): the sample parameter t = s - u_j stays fp64,
+// the cubic's derivatives and the curvature are evaluated in fp32 (FFMA + one MUFU.RSQ instead of 33 FP64
+// instructions with an fp64 square root and division), only the fp32 curvature array is written.
+template <int G, int T, int MINB, bool FIT, bool STAGED, bool F32K = false>
 __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a, FitArgs fa)
 {
+    static_assert(!F32K || (!FIT && STAGED), "the fp32 evaluation exists for the staged tridiagonal kernel");
     static_assert(32 % G == 0 && T % 32 == 0, "lanes split evenly over the candidates of a CTA");
     extern __shared__ __align__(16) unsigned char smraw[];
     __shared__ __align__(8) unsigned long long mbar;  // completion of the hand-off bulk copy
@@ -362,17 +366,35 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a, FitArgs fa)
         int j = lo;
         Rec v = REC[j * G + g];
         int inext = IB[(j + 1) * G + g];
+        [[maybe_unused]] float f1x = 0, f2x = 0, f3x = 0, fhx = 0, f1y = 0, f2y = 0, f3y = 0, fhy = 0;
+        auto narrow = [&]() {
+            if constexpr (F32K) {
+                f1x = (float)v.c1x; f2x = (float)v.c2x; f3x = (float)v.c3x; fhx = (float)v.hx;
+                f1y = (float)v.c1y; f2y = (float)v.c2y; f3y = (float)v.c3y; fhy = (float)v.hy;
+            }
+        };
+        narrow();
         for (int r = 0; r < count; ++r) {
             while (q >= inext) {
                 ++j;
                 v = REC[j * G + g];
                 inext = IB[(j + 1) * G + g];
+                narrow();
             }
             const double s = (double)q * step;
             double k;
             if constexpr (FIT) {
                 double dx, dy, ddx, ddy;
                 k = fit::curvature_at(v, s, dx, dy, ddx, ddy);
+            } else if constexpr (F32K) {
+                const float t = (float)(s - v.u);
+                const float ddx = fmaf(f3x, t, f2x), ddy = fmaf(f3y, t, f2y);
+                const float dx = fmaf(t, fmaf(fhx, t, f2x), f1x), dy = fmaf(t, fmaf(fhy, t, f2y), f1y);
+                const float cross = fabsf(fmaf(dx, ddy, -(dy * ddx)));
+                const float n2 = fmaf(dx, dx, dy * dy);
+                float rs;
+                asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(n2));
+                k = (double)(cross * rs * (rs * rs));  // exact widening: the tile and the arg-max stay fp64
             } else {
                 // |x'y'' - y'x''| / (x'^2 + y'^2)^(3/2)   (path.py:58,61), Horner form, explicit FMAs
                 const double t = s - v.u;
@@ -430,7 +452,7 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a, FitArgs fa)
                 int q = i + q0;
                 q = (q >= n) ? q - n : q;
                 const double k = KT[(size_t)q * G + g];
-                dst[(size_t)i * TILE] = k;
+                if (!F32K) dst[(size_t)i * TILE] = k;
                 if (dst32) dst32[(size_t)i * TILE] = (float)k;
             }
         } else {

@@ -561,17 +561,22 @@ def test_lockstep_cobyla_equals_serial_cobyla():
 
 
 @pytest.mark.parametrize("name", ["buckmore_tbr18_bayes", "buckmore_mx5_bayes"])
-def test_fp32_sweep_variant(name):
-    """The optional fp32 variant of the sweeps (north_star tolerance 1e-4): against the fp64 kernels on 65,536
-    candidates and against the reference's golden lap times."""
+def test_fp32_sweep_variant(name, golden):
+    """The optional fp32 variant (north_star tolerance 1e-4: fp32 curvature evaluation and fp32 sweeps on the fp64
+    spline): against the fp64 kernels on 65,536 candidates, against the C oracle, and against the unmodified
+    reference's golden lap times."""
     ev, co = make(name)
     a = np.random.default_rng(32).uniform(0.0, 0.99, (65536, ev.n_alpha))
     l64 = ev.lap_times(a)
     ev.set_sweep_precision(32)
     l32 = ev.lap_times(a)
     rel = rel_err(l32, l64)
-    print(f"fp32 sweeps vs fp64 ({name}): median {np.median(rel):.2e}, p99 {np.percentile(rel, 99):.2e}, max {rel.max():.2e}")
+    print(f"fp32 variant vs fp64 ({name}): median {np.median(rel):.2e}, p99 {np.percentile(rel, 99):.2e}, max {rel.max():.2e}")
     assert rel.max() <= 1e-4 and np.median(rel) <= 2e-5
+    assert rel_err(l32[:8192], co.lap_times(a[:8192])).max() <= 1e-4
+    g = golden(name)
+    assert rel_err(ev.lap_times(g["alphas"]), g["laps"]).max() <= 1e-4  # the reference itself
+    assert np.array_equal(ev.topk(torch.as_tensor(l32).cuda(), 10)[1], top_k(list(l32), 10)[0])
     ev.set_sweep_precision(64)
     assert np.array_equal(ev.lap_times(a), l64)
     ev.close()
