@@ -540,7 +540,7 @@ def run_ours(args):
         variants["fp32_sweeps"] = short_run(D, ev, dev_sets, d_laps, vsteps, LANES, base, finish)
         kt32 = ev.kernel_times(dev_sets[0], d_lap, reps=3)
         n_ = ns - 1
-        b32 = 8 * na + 12 * n_ + 16 * n_ + 8
+        b32 = 8 * na + 4 * n_ + 16 * n_ + 8  # K1b writes the fp32 curvature only; the sweeps read it twice, park 4-byte velocities
         variants["fp32_sweeps"].update({"kernel_ms": {k: round(v, 4) for k, v in kt32.items()}, "bytes_per_candidate": b32,
                                         "hbm_frac": b32 * B / (variants["fp32_sweeps"]["ms_per_step"] * 1e-3) / 1e9 / peak,
                                         "tolerance": "1e-4 relative to the fp64 kernels"})
@@ -565,9 +565,9 @@ def run_ours(args):
         n = ns - 1
         # algorithmic bytes per candidate of each kernel: the shares of A_staged;
         # the K1a -> K1b hand-off (second derivatives, knots) is not in the model and not counted
-        # fp32 sweeps read K1b's 4-byte copy of the curvature and park 4-byte velocities
+        # fp32 variant: K1b evaluates and writes a 4-byte curvature, the sweeps read it and park 4-byte velocities
         sweep_bytes = 32 * n + 8 if args.sweep_bits == 64 else 16 * n + 8
-        k1b_bytes = 8 * n if args.sweep_bits == 64 else 12 * n
+        k1b_bytes = 8 * n if args.sweep_bits == 64 else 4 * n
         alg = {"k1a_spline_solve": 8 * na, "k1b_curvature": k1b_bytes, "k23_sweep": sweep_bytes}
         dom = max(kt, key=lambda k: kt[k])
         achieved = alg[dom] * B / (kt[dom] * 1e-3) / 1e9
