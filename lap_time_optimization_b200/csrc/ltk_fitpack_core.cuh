@@ -382,51 +382,66 @@ LTK_HD void solve(int N, const Io& io, Points pts)
     const double cMx = fdiv(W0.zx - cNx * W0.b, W0.a), cMy = fdiv(W0.zy - cNy * W0.b, W0.a);
     LTK_CX(N) = cNx; LTK_CY(N) = cNy; LTK_CX(N - 1) = cMx; LTK_CY(N - 1) = cMy;
     double c1x = 0, c2x = 0, c1y = 0, c2y = 0;  // c(i+1), c(i+2)
-    // the next row is fetched before the current one's divisions: the loads do not wait for the chain
-    double ra = LTK_R(n10, 0), rb = LTK_R(n10, 1), rc = LTK_R(n10, 2), re1 = LTK_R(n10, 3), re2 = LTK_R(n10, 4),
-           rzx = LTK_R(n10, 5), rzy = LTK_R(n10, 6);
-    constexpr int AHEAD = 4;  // rows fetched into L1 ahead of the register look-ahead
-    for (int i = n10 - 1; i >= 1 && i >= n10 - AHEAD; --i)
-        for (int e = 0; e < 7; ++e) prefetch(&LTK_R(i, e));
-    for (int i = n10; i >= 1; --i) {
-        const double a = ra, b = rb, cc = rc, e1 = re1, e2 = re2;
-        double sx = rzx, sy = rzy;
-        if (i - 1 - AHEAD >= 1)
-            for (int e = 0; e < 7; ++e) prefetch(&LTK_R(i - 1 - AHEAD, e));
-        if (i > 1) {
-            ra = LTK_R(i - 1, 0); rb = LTK_R(i - 1, 1); rc = LTK_R(i - 1, 2); re1 = LTK_R(i - 1, 3);
-            re2 = LTK_R(i - 1, 4); rzx = LTK_R(i - 1, 5); rzy = LTK_R(i - 1, 6);
+    // The factor rows come back from the global scratch (written by this thread during the forward pass, by now in
+    // L2 or DRAM: ~1,000 cycles) while one step of the recurrence is ~150 cycles, and a warp issues in order: the
+    // loads of BU rows are issued together, then the BU dependent steps run (ncu: 20 % of the kernel's stall samples
+    // were these loads when each row was fetched one step ahead).
+    constexpr int BU = 6;
+    for (int i0 = n10; i0 >= 1; i0 -= BU) {
+        double ra[BU], rb[BU], rc[BU], re1[BU], re2[BU], rzx[BU], rzy[BU];
+#pragma unroll
+        for (int u = 0; u < BU; ++u) {
+            const int i = (i0 - u >= 1) ? i0 - u : 1;  // clamped: the surplus loads of the last block are not used
+            ra[u] = LTK_R(i, 0); rb[u] = LTK_R(i, 1); rc[u] = LTK_R(i, 2); re1[u] = LTK_R(i, 3);
+            re2[u] = LTK_R(i, 4); rzx[u] = LTK_R(i, 5); rzy[u] = LTK_R(i, 6);
         }
-        sx = sx - cMx * e1; sx = sx - cNx * e2;
-        sy = sy - cMy * e1; sy = sy - cNy * e2;
-        if (i <= n10 - 1) { sx = sx - c1x * b; sy = sy - c1y * b; }
-        if (i <= n10 - 2) { sx = sx - c2x * cc; sy = sy - c2y * cc; }
-        fdiv2(sx, a, sy, a, sx, sy);
-        c2x = c1x; c2y = c1y; c1x = sx; c1y = sy;
-        LTK_CX(i) = sx; LTK_CY(i) = sy;
+#pragma unroll
+        for (int u = 0; u < BU; ++u) {
+            const int i = i0 - u;
+            if (i >= 1) {
+                double sx = rzx[u], sy = rzy[u];
+                sx = sx - cMx * re1[u]; sx = sx - cNx * re2[u];
+                sy = sy - cMy * re1[u]; sy = sy - cNy * re2[u];
+                if (i <= n10 - 1) { sx = sx - c1x * rb[u]; sy = sy - c1y * rb[u]; }
+                if (i <= n10 - 2) { sx = sx - c2x * rc[u]; sy = sy - c2y * rc[u]; }
+                fdiv2(sx, ra[u], sy, ra[u], sx, sy);
+                c2x = c1x; c2y = c1y; c1x = sx; c1y = sy;
+                LTK_CX(i) = sx; LTK_CY(i) = sy;
+            }
+        }
     }
     for (int q = 1; q <= 3; ++q) { LTK_CX(N + q) = LTK_CX(q); LTK_CY(N + q) = LTK_CY(q); }
     // splder: wrk1(i) = 3 (c(i+1) - c(i)) / (t(i+4) - t(i+1)),  wrk2(i) = 2 (wrk1(i+1) - wrk1(i)) / (t(i+4) - t(i+2))
-    for (int i = 3; i <= 2 + AHEAD; ++i) { prefetch(&LTK_CX(i)); prefetch(&LTK_CY(i)); }
+    // same blocking for the coefficient loads of the two derivative passes (c(N + q) = c(q) were just stored)
     double px_ = LTK_CX(1), py_ = LTK_CY(1), w1px = 0, w1py = 0;
-    double nx = LTK_CX(2), ny = LTK_CY(2);
-    for (int i = 1; i <= N + 2; ++i) {
-        const double cx1 = nx, cy1 = ny;
-        if (i + 2 + AHEAD <= N + 3) { prefetch(&LTK_CX(i + 2 + AHEAD)); prefetch(&LTK_CY(i + 2 + AHEAD)); }
-        if (i <= N + 1) { nx = LTK_CX(i + 2); ny = LTK_CY(i + 2); }  // fetched one iteration ahead
-        const double fac = LTK_T(i + 4) - LTK_T(i + 1);
-        double w1x, w1y;
-        fdiv2(3.0 * (cx1 - px_), fac, 3.0 * (cy1 - py_), fac, w1x, w1y);
-        io.w1x[(long)(i - 1) * io.sw] = w1x;
-        io.w1y[(long)(i - 1) * io.sw] = w1y;
-        if (i >= 2) {  // wrk2(i-1) from wrk1(i-1), wrk1(i): knots t(i+3), t(i+1)
-            const double fac2 = LTK_T(i + 3) - LTK_T(i + 1);
-            double w2x, w2y;
-            fdiv2(2.0 * (w1x - w1px), fac2, 2.0 * (w1y - w1py), fac2, w2x, w2y);
-            io.w2x[(long)(i - 2) * io.sw] = w2x;
-            io.w2y[(long)(i - 2) * io.sw] = w2y;
+    constexpr int WU = 8;
+    for (int ib = 1; ib <= N + 2; ib += WU) {
+        double nxs[WU], nys[WU];
+#pragma unroll
+        for (int u = 0; u < WU; ++u) {
+            const int i = (ib + u <= N + 2) ? ib + u : N + 2;
+            nxs[u] = LTK_CX(i + 1); nys[u] = LTK_CY(i + 1);
         }
-        w1px = w1x; w1py = w1y; px_ = cx1; py_ = cy1;
+#pragma unroll
+        for (int u = 0; u < WU; ++u) {
+            const int i = ib + u;
+            if (i <= N + 2) {
+                const double cx1 = nxs[u], cy1 = nys[u];
+                const double fac = LTK_T(i + 4) - LTK_T(i + 1);
+                double w1x, w1y;
+                fdiv2(3.0 * (cx1 - px_), fac, 3.0 * (cy1 - py_), fac, w1x, w1y);
+                io.w1x[(long)(i - 1) * io.sw] = w1x;
+                io.w1y[(long)(i - 1) * io.sw] = w1y;
+                if (i >= 2) {  // wrk2(i-1) from wrk1(i-1), wrk1(i): knots t(i+3), t(i+1)
+                    const double fac2 = LTK_T(i + 3) - LTK_T(i + 1);
+                    double w2x, w2y;
+                    fdiv2(2.0 * (w1x - w1px), fac2, 2.0 * (w1y - w1py), fac2, w2x, w2y);
+                    io.w2x[(long)(i - 2) * io.sw] = w2x;
+                    io.w2y[(long)(i - 2) * io.sw] = w2y;
+                }
+                w1px = w1x; w1py = w1y; px_ = cx1; py_ = cy1;
+            }
+        }
     }
 #undef LTK_CX
 #undef LTK_CY
