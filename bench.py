@@ -165,13 +165,32 @@ def run_reference(args):
 # clocks
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region: NVML polled every 2 ms from a thread (the timed region
+    of a 20-step run is 15 ms: nvidia-smi's 20 ms loop gave it one sample); nvidia-smi -lms as the fallback."""
+
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.nvml, self.stop_flag = [], None, index, None, False
 
     def start(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: map through CUDA_VISIBLE_DEVICES when it lists indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [v for v in vis.split(",") if v.strip().isdigit()]
+            phys = int(ids[self.index]) if self.index < len(ids) else self.index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "20"],
@@ -181,11 +200,35 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        bits = {"hw_slowdown": int(getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8)),
+                "hw_thermal_slowdown": int(getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40)),
+                "sw_thermal_slowdown": int(getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20)),
+                "sw_power_cap": int(getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4))}
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                mask = int(get_reasons(self.handle))
+                self.rows.append((time.perf_counter(), mhz, [k for k, b in bits.items() if mask & b]))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for ln in self.proc.stdout:
             self.rows.append((time.perf_counter(), ln.strip()))
 
     def stop(self, t0, t1):
+        if self.nvml is not None:
+            time.sleep(0.01)
+            self.stop_flag = True
+            picked = [r for r in self.rows if t0 <= r[0] <= t1] or self.rows[-3:]
+            sm = [r[1] for r in picked]
+            reasons = sorted({x for r in picked for x in r[2]})
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                    "samples": len(picked), "source": "nvml, 2 ms polling"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.12)
@@ -203,7 +246,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(picked)}
+                "samples": len(picked), "source": "nvidia-smi -lms 20"}
 
 
 def fp64_pipe_model(args, B, n, ms_per_step, clocks):
