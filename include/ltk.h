@@ -176,6 +176,17 @@ int ltk_profile(ltk_ctx *ctx, const double *d_alpha, double *d_s, double *d_k, d
 int ltk_topk(ltk_ctx *ctx, const double *d_lap, int64_t B, int64_t index_base, int k,
              double *d_best_lap, int64_t *d_best_idx, void *stream);
 
+/* alphas -> lap times AND the population's k best in one call: what the random-population stage does with its
+ * scores, `sorted(zip(taus, alphas), key=tau)[0:10]` after the scoring loop
+ * (trajectory_bayesian_nonlinear.py:236-257).  Same results as ltk_eval_alphas followed by ltk_topk on the same
+ * stream; the selection runs in the epilogue of the sweep kernel (every CTA selects its own k best from the lap
+ * times it holds in registers, the CTA that finishes last merges them) -- three kernel launches per population
+ * instead of four, no second pass over d_lap.  Falls back to the separate selection kernel where the fused
+ * merge does not fit (k > 16, populations beyond ~600,000 candidates per call, the fp32 sweep variant). */
+int ltk_eval_alphas_topk(ltk_ctx *ctx, const double *d_alphas, int64_t B, double *d_lap, void *d_workspace,
+                         size_t workspace_bytes, int64_t index_base, int k, double *d_best_lap,
+                         int64_t *d_best_idx, void *stream);
+
 /* Path facade (path.py:17-77): evaluate the periodic spline through m-1 unique points
  * d_xy [2][m] (closed; last column ignored) with knots d_knots [m] (Path.dists) at n parameters d_u.
  * Any of the outputs may be NULL. d_gamma2[1] receives sum(k^2) (path.py:63-77). */

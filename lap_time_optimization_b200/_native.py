@@ -48,6 +48,7 @@ SIGNATURES = {
     "ltk_set_sweep_split": (C.c_int, [_vp, C.c_int]),
     "ltk_workspace_bytes": (C.c_int, [_vp, C.c_int64, C.POINTER(C.c_size_t)]),
     "ltk_eval_alphas": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, C.c_size_t, _vp]),
+    "ltk_eval_alphas_topk": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, C.c_size_t, C.c_int64, C.c_int, _vp, _vp, _vp]),
     "ltk_eval_alphas_host": (C.c_int, [_vp, _vp, C.c_int64, _vp]),
     "ltk_eval_alphas_timed": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, C.c_size_t, _vp, C.POINTER(C.c_float)]),
     "ltk_eval_objectives": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _vp, C.c_size_t, _vp]),

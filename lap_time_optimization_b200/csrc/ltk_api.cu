@@ -31,7 +31,8 @@ struct ltk_ctx {
     double* d_topk_lap[2];  // ping-pong scratch of the top-k stages, grown on demand
     long long* d_topk_idx[2];
     long long topk_cap;     // entries per scratch buffer
-    unsigned* d_ticket;     // "last block finishes" counter of the single-launch top-k
+    unsigned* d_ticket;     // [TICKET_CAP] "last block finishes" counters (zero between launches): [0] global, then
+                            // one per group of the selection fused into the sweeps (ltk_topk_fused.cuh)
     cudaStream_t aux_stream;  // the remainder sweep (see run_pipeline) runs next to the main one
     cudaEvent_t aux_ev[2];
     int sweep_remainder;      // 0 disables the split (LTK_SWEEP_REMAINDER=0)
@@ -392,6 +393,7 @@ cudaError_t launch_k1f_cfg(const K1FConfig& c, const K1Args& a, const FitArgs& f
             static const bool f32k = !(getenv("LTK_K1B_F32") && atoi(getenv("LTK_K1B_F32")) == 0);
             if (a.kap32 && f32k) return launch_k1f<4, 256, 4, false, true, true>(a, fa, c.smem, st);
         }
+        if (m == 5) return launch_k1f<4, 256, 5, FIT>(a, fa, c.smem, st);
         if (m == 3) return launch_k1f<4, 256, 3, FIT>(a, fa, c.smem, st);
         if (m == 2) return launch_k1f<4, 256, 2, FIT>(a, fa, c.smem, st);
         return launch_k1f<4, 256, 4, FIT>(a, fa, c.smem, st);
@@ -431,8 +433,20 @@ cudaError_t launch_k1b_cfg(const K1Config& c, const K1Args& a, cudaStream_t st)
     return launch_k1b<8, 512>(a, c.smem, st);
 }
 
+// top-k of the population the pipeline scores, wanted together with the lap times: run_pipeline fuses the
+// selection into the sweep kernels' epilogue where it can and says so in `fused`
+struct TopkReq {
+    int k;
+    long long index_base;
+    double* best_lap;
+    long long* best_idx;
+    bool fused;
+};
+constexpr int TICKET_CAP = 1 + 1024;
+int ensure_topk_scratch(ltk_ctx* ctx, long long entries, cudaStream_t st);
+
 int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m, long long B, double* d_lap, char* ws,
-                 const WsLayout& w, bool dumps, cudaStream_t st, cudaEvent_t* ev, bool k1_only);
+                 const WsLayout& w, bool dumps, cudaStream_t st, cudaEvent_t* ev, bool k1_only, TopkReq* topk = nullptr);
 
 // the pipeline launches on a laid-out workspace
 int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m, long long B,
@@ -444,8 +458,9 @@ int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m
 
 int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m, long long B,
                  double* d_lap, char* ws, const WsLayout& w, bool dumps, cudaStream_t st,
-                 cudaEvent_t* ev, bool k1_only)
+                 cudaEvent_t* ev, bool k1_only, TopkReq* topk)
 {
+    if (topk) topk->fused = false;
     K1Config cfg;
     K1FConfig fcfg;
     const bool k1_one_kernel = pick_k1f(ctx, &fcfg);
@@ -555,8 +570,30 @@ int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m
         const long long rest = w.Bp - whole;
         const bool split = !roles && !dumps && ctx->sweep_mode == 0 && ctx->sweep_remainder && ctx->aux_stream &&
                            whole > 0 && rest > 0 && 2 * rest <= layer + layer / 8;
+        // the selection of the k best rides in the sweep CTAs' epilogue when the two merge stages fit one CTA each
+        f.tk.k = 0;
+        static const bool fuse_off = getenv("LTK_TOPK_FUSED") && atoi(getenv("LTK_TOPK_FUSED")) == 0;
+        if (topk && !dumps && !fuse_off && topk->k >= 1 && topk->k <= FUSE_K_MAX) {
+            const long long n_slots = roles ? (long long)gridr : split ? whole / FUSED_THREADS + rest / 32 : (long long)gridf;
+            const long long cap = (long long)FUSE_THREADS * FUSE_E / topk->k;  // keys one merge stage takes
+            long long group = 1;
+            while (group * group < n_slots) ++group;
+            const long long n_groups = (n_slots + group - 1) / group;
+            if (group <= cap && n_groups <= cap && 1 + n_groups <= TICKET_CAP) {
+                int rc = ensure_topk_scratch(ctx, (n_slots + n_groups) * topk->k, st);
+                if (rc != LTK_OK) return rc;
+                f.tk.mid_lap = ctx->d_topk_lap[0]; f.tk.mid_idx = ctx->d_topk_idx[0];
+                f.tk.tickets = ctx->d_ticket;
+                f.tk.out_lap = topk->best_lap; f.tk.out_idx = topk->best_idx;
+                f.tk.index_base = topk->index_base; f.tk.k = topk->k;
+                f.tk.slot_base = 0;
+                f.tk.n_slots = (int)n_slots; f.tk.group = (int)group; f.tk.n_groups = (int)n_groups;
+                topk->fused = true;
+            }
+        }
         if (split) {
             f.first = whole; f.last = w.Bp;
+            f.tk.slot_base = (int)(whole / FUSED_THREADS);  // the remainder's CTAs take the slots after the main launch's
             LTK_CUDA(ctx, cudaEventRecord(ctx->aux_ev[0], st));
             LTK_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_ev[0], 0));
             unsigned gr = (unsigned)(rest / 32);
@@ -570,6 +607,7 @@ int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m
             g_launches.fetch_add(1);
             LTK_CUDA(ctx, cudaEventRecord(ctx->aux_ev[1], ctx->aux_stream));
             f.first = 0; f.last = whole;
+            f.tk.slot_base = 0;
             gridf = (unsigned)(whole / FUSED_THREADS);
         }
         trace_open(LTK_TRACE_K23, st);
@@ -599,28 +637,40 @@ int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m
 
 // top-k of `count` keys.  Up to TOPK_BLOCK_KEYS / k blocks: ONE launch (the block that finishes last
 // merges every block's winners); beyond that, stages chained until few enough blocks are left.
-int run_topk(ltk_ctx* ctx, const double* d_lap, const long long* d_idx, long long count, long long index_base, int k,
-             double* d_best_lap, long long* d_best_idx, cudaStream_t st)
+// scratch of the top-k stages (two ping-pong buffers of `entries` keys) and the ticket counters; grows on demand
+// (rare: first call / larger population -- the stream is drained before the old buffers are freed)
+int ensure_topk_scratch(ltk_ctx* ctx, long long entries, cudaStream_t st)
 {
-    long long blocks = (count + TOPK_BLOCK_KEYS - 1) / TOPK_BLOCK_KEYS;
-    if (blocks < 1) blocks = 1;
-    if (blocks > 1 && blocks * k > ctx->topk_cap) {  // grow the scratch (rare: first call / larger population)
-        LTK_CUDA(ctx, cudaStreamSynchronize(st));
+    if (entries > ctx->topk_cap) {
+        LTK_CUDA(ctx, cudaDeviceSynchronize());  // a split sweep of an earlier call may still use the scratch on the aux stream
         for (int i = 0; i < 2; ++i) {
             cudaFree(ctx->d_topk_lap[i]); cudaFree(ctx->d_topk_idx[i]);
             ctx->d_topk_lap[i] = nullptr; ctx->d_topk_idx[i] = nullptr;
         }
         ctx->topk_cap = 0;
-        const long long cap = blocks * TOPK_MAX;
+        long long cap = 16384;
+        while (cap < entries) cap *= 2;
         for (int i = 0; i < 2; ++i) {
             LTK_CUDA(ctx, cudaMalloc(&ctx->d_topk_lap[i], sizeof(double) * cap));
             LTK_CUDA(ctx, cudaMalloc(&ctx->d_topk_idx[i], sizeof(long long) * cap));
         }
         ctx->topk_cap = cap;
     }
-    if (blocks > 1 && !ctx->d_ticket) {
-        LTK_CUDA(ctx, cudaMalloc(&ctx->d_ticket, sizeof(unsigned)));
-        LTK_CUDA(ctx, cudaMemsetAsync(ctx->d_ticket, 0, sizeof(unsigned), st));
+    if (!ctx->d_ticket) {
+        LTK_CUDA(ctx, cudaMalloc(&ctx->d_ticket, sizeof(unsigned) * TICKET_CAP));
+        LTK_CUDA(ctx, cudaMemsetAsync(ctx->d_ticket, 0, sizeof(unsigned) * TICKET_CAP, st));
+    }
+    return LTK_OK;
+}
+
+int run_topk(ltk_ctx* ctx, const double* d_lap, const long long* d_idx, long long count, long long index_base, int k,
+             double* d_best_lap, long long* d_best_idx, cudaStream_t st)
+{
+    long long blocks = (count + TOPK_BLOCK_KEYS - 1) / TOPK_BLOCK_KEYS;
+    if (blocks < 1) blocks = 1;
+    if (blocks > 1) {
+        int rc = ensure_topk_scratch(ctx, blocks * (long long)k, st);
+        if (rc != LTK_OK) return rc;
     }
     int pp = 0;
     while (true) {
@@ -644,6 +694,14 @@ int run_topk(ltk_ctx* ctx, const double* d_lap, const long long* d_idx, long lon
 }  // namespace
 
 extern "C" {
+
+#ifdef LTK_K1B_CLOCK
+// developer build only (not in include/ltk.h): the K1b phase time stamps of the last launch
+int ltk_debug_k1b_clocks(long long* h_out, long long count)
+{
+    return cudaMemcpyFromSymbol(h_out, g_k1b_clock, sizeof(long long) * count) == cudaSuccess ? 0 : -2;
+}
+#endif
 
 int ltk_version(void) { return 100; }
 int64_t ltk_launch_count(void) { return (int64_t)g_launches.load(); }
@@ -859,6 +917,25 @@ int ltk_eval_alphas(ltk_ctx* ctx, const double* d_alphas, int64_t B, double* d_l
     DeviceGuard guard(ctx->device);
     return run_pipeline(ctx, d_alphas, nullptr, 0, B, d_lap, static_cast<char*>(d_workspace), w, false,
                         static_cast<cudaStream_t>(stream));
+}
+
+int ltk_eval_alphas_topk(ltk_ctx* ctx, const double* d_alphas, int64_t B, double* d_lap, void* d_workspace,
+                         size_t workspace_bytes, int64_t index_base, int k, double* d_best_lap, int64_t* d_best_idx,
+                         void* stream)
+{
+    if (!ctx) return LTK_E_ARG;
+    if (!d_alphas || !d_lap || !d_workspace || !d_best_lap || !d_best_idx || B < 1)
+        return fail(ctx, LTK_E_ARG, "null argument or empty population");
+    if (k < 1 || k > TOPK_MAX) return fail(ctx, LTK_E_ARG, "k must be in 1..64");
+    WsLayout w = ctx_layout(ctx, B, false);
+    if (workspace_bytes < w.total) return fail(ctx, LTK_E_WORKSPACE, "workspace too small (see ltk_workspace_bytes)");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TopkReq req{k, (long long)index_base, d_best_lap, reinterpret_cast<long long*>(d_best_idx), false};
+    int rc = run_pipeline(ctx, d_alphas, nullptr, 0, B, d_lap, static_cast<char*>(d_workspace), w, false, st, nullptr,
+                          false, &req);
+    if (rc != LTK_OK || req.fused) return rc;
+    return run_topk(ctx, d_lap, nullptr, B, index_base, k, d_best_lap, reinterpret_cast<long long*>(d_best_idx), st);
 }
 
 // Host in, host out, one call: the latency path of the optimiser loops (finite-difference rounds of

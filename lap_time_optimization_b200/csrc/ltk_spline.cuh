@@ -28,6 +28,23 @@
 
 namespace ltk {
 
+#ifndef LTK_K1B_TRIM
+#define LTK_K1B_TRIM 15  // bit set of the trims below (A/B): 1 packed record, 2 guessed chunk start, 4 write-out, 8 step
+#endif
+// Interval record of k1b_samples (tridiagonal mode), 64 bytes = four 16-byte shared loads:
+// S'(t) = c1 + t (c2 + t h),  S''(t) = c2 + c3 t;  h = c3 / 2 is formed on load (exact), the index of the next
+// interval's first sample rides in the last slot.
+struct __align__(16) IntervalP {
+    double u, c1x, c1y, c2x, c2y, c3x, c3y;
+    int inext, pad;
+    double pad2[2];  // 80-byte stride: the G records of a row then fall in distinct banks (64 bytes: two-way conflicts)
+};
+static_assert(sizeof(IntervalP) == 80, "IntervalP must be 80 bytes");
+constexpr bool K1B_TRIM = (LTK_K1B_TRIM & 1) != 0;      // packed record
+constexpr bool K1B_GUESS = (LTK_K1B_TRIM & 2) != 0;     // chunk start interval from a proportional guess
+constexpr bool K1B_WLIN = (LTK_K1B_TRIM & 4) != 0;      // write-out with linear cursors
+constexpr bool K1B_STEP = (LTK_K1B_TRIM & 8) != 0;      // sampling step once per candidate
+
 __host__ __device__ inline int k1_chunk(int n, int cpt)
 {
     int c = (n + cpt - 1) / cpt;
@@ -44,10 +61,10 @@ __host__ __device__ inline size_t k1f_smem_bytes(int G, int threads, int N, int 
                                                  bool staged = true)
 {
     size_t tile = staged ? (size_t)(ns - 1) * G : 0, scr = k1f_scratch_doubles(G, N, fitpack);
-    size_t bytes = (size_t)N * G * (fitpack ? sizeof(fit::FitInterval) : sizeof(Interval));  // interval records [N][G]
+    size_t bytes = (size_t)N * G * (fitpack ? sizeof(fit::FitInterval) : K1B_TRIM ? sizeof(IntervalP) : sizeof(Interval));  // interval records [N][G]
     bytes += (tile > scr ? tile : scr) * sizeof(double);             // curvature tile | scratch
     bytes += (size_t)(N + 1) * G * sizeof(int) + 8;                  // first sample index of each interval (+ alignment)
-    bytes += (size_t)G * (sizeof(double) + sizeof(int));             // length, rotation
+    bytes += (size_t)G * (2 * sizeof(double) + sizeof(int));         // length, sampling step, rotation
     bytes += (size_t)(threads / 32) * G * (sizeof(double) + sizeof(int));  // arg-max partials
     return (bytes + 15) / 16 * 16;
 }
@@ -181,6 +198,21 @@ __global__ void __launch_bounds__(K1A_THREADS, 4) k1a_solve(K1Args a)
 // ------------------------------------------------------------------------------------------------
 // K1b
 // ------------------------------------------------------------------------------------------------
+#ifdef LTK_K1B_CLOCK  // developer build: phase time stamps of every CTA (scripts/k1b_phase_probe.py)
+constexpr int K1B_CLOCK_SLOTS = 8;
+__device__ long long g_k1b_clock[K1B_CLOCK_SLOTS * 65536];
+__device__ __forceinline__ void k1b_stamp(int slot)
+{
+    if (threadIdx.x == 0 && blockIdx.x < 65536) {
+        long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_k1b_clock[(size_t)blockIdx.x * K1B_CLOCK_SLOTS + slot] = t;
+    }
+}
+#define K1B_STAMP(slot) k1b_stamp(slot)
+#else
+#define K1B_STAMP(slot)
+#endif
 // FIT = true: the records and the per-sample arithmetic of the FITPACK mode (ltk_fitpack_core.cuh); the
 // hand-off arrays are then K1a-F's knots t [N+7] and derivative coefficients wrk1 [N+2], wrk2 [N+1] per coordinate.
 // STAGED = false: two passes over the samples instead of the shared-memory tile -- the first finds the rotation,
@@ -200,13 +232,16 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a, FitArgs fa)
     __shared__ __align__(8) unsigned long long mbar;  // completion of the hand-off bulk copy
     const int N = a.N, n = a.ns - 1, NG = N * G;
     constexpr int NW = T / 32, CPT = T / G;
-    using Rec = typename std::conditional<FIT, fit::FitInterval, Interval>::type;
+    using Rec = typename std::conditional<FIT, fit::FitInterval,
+                                          typename std::conditional<K1B_TRIM, IntervalP, Interval>::type>::type;
+    constexpr bool PACKED = !FIT && K1B_TRIM;  // the record carries the next interval's first sample index
     Rec* REC = reinterpret_cast<Rec*>(smraw);
     double* KT = reinterpret_cast<double*>(REC + NG);
     const size_t tile = STAGED ? (size_t)n * G : 0, scr = k1f_scratch_doubles(G, N, FIT);
     int* IB = reinterpret_cast<int*>(KT + ((STAGED && tile > scr) ? tile : scr));   // [N+1][G]
     double* LEN = reinterpret_cast<double*>(IB + (N + 1) * G + (((N + 1) * G) & 1));
-    double* RV = LEN + G;                                               // [NW][G]
+    double* STEP = LEN + G;                                             // [G] np.linspace step (tbn.py:71)
+    double* RV = STEP + G;                                              // [NW][G]
     int* RI = reinterpret_cast<int*>(RV + NW * G);                      // [NW][G]
     int* ROT = RI + NW * G;                                             // [G]
     // scratch inside the tile region (dead before the first curvature is stored)
@@ -225,6 +260,7 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a, FitArgs fa)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long b0 = (long long)blockIdx.x * G;
+    K1B_STAMP(0);
 
     if constexpr (FIT) {
         // ---- L (FITPACK mode): everything comes from K1a-F: one bulk copy of the group's packed block (G = 4),
@@ -247,7 +283,7 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a, FitArgs fa)
             }
             __syncthreads();
         }
-        if (tid < G) LEN[tid] = U[NG + tid];
+        if (tid < G) { LEN[tid] = U[NG + tid]; STEP[tid] = U[NG + tid] / (double)(a.ns - 1); }
         __syncthreads();
         // ---- C (FITPACK mode): per-interval record (splder / fpbspl operands) and first sample index ---------
         for (int idx = tid; idx < NG; idx += T) {
@@ -265,7 +301,7 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a, FitArgs fa)
             rec.pad = 0.0;
             REC[idx] = rec;
             const double u0 = rec.t0;
-            const double step = LEN[g] / (double)(a.ns - 1);  // np.linspace step (tbn.py:71)
+            const double step = K1B_STEP ? STEP[g] : LEN[g] / (double)(a.ns - 1);  // np.linspace step (tbn.py:71)
             int i = 0;
             if (j > 0) {
                 i = (int)ddiv<false>(u0, step);
@@ -312,8 +348,9 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a, FitArgs fa)
             }
             __syncthreads();
         }
-        if (tid < G) LEN[tid] = U[NG + tid];
+        if (tid < G) { LEN[tid] = U[NG + tid]; STEP[tid] = U[NG + tid] / (double)(a.ns - 1); }
         __syncthreads();
+        K1B_STAMP(1);
         // ---- C: per-interval coefficients  S'(t) = c1 + t (c2 + t h),  S''(t) = c2 + c3 t,  h = c3/2, and the
         //      first sample index of every interval: IB[j] = min{ i : fl(i*step) >= U[j] } ------------------
         for (int idx = tid; idx < NG; idx += T) {
@@ -323,15 +360,20 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a, FitArgs fa)
             const double mx = RX[idx], mxn = RX[jn * G + g];
             const double my = RY[idx], myn = RY[jn * G + g];
             const double c3x = ddiv<false>(mxn - mx, h), c3y = ddiv<false>(myn - my, h);
-            Interval rec;
-            rec.u = u0; rec.unext = u1;
+            Rec rec;
+            rec.u = u0;
             rec.c1x = ddiv<false>(PX[jn * G + g] - PX[idx], h) - ddiv<false>(h * (2.0 * mx + mxn), 6.0);
             rec.c1y = ddiv<false>(PY[jn * G + g] - PY[idx], h) - ddiv<false>(h * (2.0 * my + myn), 6.0);
             rec.c2x = mx; rec.c2y = my;
             rec.c3x = c3x; rec.c3y = c3y;
-            rec.hx = 0.5 * c3x; rec.hy = 0.5 * c3y;
-            REC[idx] = rec;
-            const double step = LEN[g] / (double)(a.ns - 1);  // np.linspace step (tbn.py:71)
+            if constexpr (PACKED) {
+                rec.pad = 0;
+            } else {
+                rec.unext = u1;
+                rec.hx = 0.5 * c3x; rec.hy = 0.5 * c3y;
+                REC[idx] = rec;
+            }
+            const double step = K1B_STEP ? STEP[g] : LEN[g] / (double)(a.ns - 1);  // np.linspace step (tbn.py:71)
             int i = 0;
             if (j > 0) {
                 i = (int)ddiv<false>(u0, step);
@@ -341,16 +383,29 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a, FitArgs fa)
             }
             IB[idx] = i;
             if (j == N - 1) IB[NG + g] = n;
+            if constexpr (PACKED) {
+                // the next interval's first sample: the same search for the knot u1 (interval N-1 ends at n)
+                int in = n;
+                if (j + 1 < N) {
+                    in = (int)ddiv<false>(u1, step);
+                    in = max(0, min(in, n));
+                    while (in < n && (double)in * step < u1) ++in;
+                    while (in > 0 && (double)(in - 1) * step >= u1) --in;
+                }
+                rec.inext = in;
+                REC[idx] = rec;
+            }
         }
         __syncthreads();  // scratch is dead from here on: the tile region now takes curvatures
     }
+    K1B_STAMP(2);
 
     // ---- K: curvature at the samples ----------------------------------------------------------------------
     const int g = tid % G, c = tid / G;
     // balanced chunks: every thread of a candidate gets n / CPT samples, the first n % CPT one more
     const int cbase = n / CPT, cextra = n - cbase * CPT;
     const int i0 = c * cbase + min(c, cextra), i1 = i0 + cbase + (c < cextra ? 1 : 0);
-    const double step = LEN[g] / (double)(a.ns - 1);
+    const double step = K1B_STEP ? STEP[g] : LEN[g] / (double)(a.ns - 1);
     // One flat loop per run of samples: every lane of the warp runs the same number of iterations (nested
     // per-interval loops diverge -- interval boundaries differ from lane to lane -- and ran at 19 of
     // 32 lanes); the interval switch is an integer test that fires about once per 20 samples, the wrap of the
@@ -358,19 +413,35 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a, FitArgs fa)
     auto walk = [&](int qa, int count, auto&& sink) {  // samples qa, qa+1, ... (mod n) of candidate g
         if (count <= 0) return;
         int q = (qa >= n) ? qa - n : qa;
-        int lo = 0, hi = N - 1;  // interval of sample q: largest j with IB[j] <= q
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (IB[mid * G + g] <= q) lo = mid; else hi = mid - 1;
+        int j;  // interval of sample q: largest j with IB[j] <= q
+        if constexpr (K1B_GUESS) {
+            // the knots follow the track's own spacing: start from the proportional guess and walk (a step or two)
+            j = min(N - 1, (int)(((long long)q * N) / n));
+            while (j + 1 < N && IB[(j + 1) * G + g] <= q) ++j;
+            while (j > 0 && IB[j * G + g] > q) --j;
+        } else {
+            int lo = 0, hi = N - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (IB[mid * G + g] <= q) lo = mid; else hi = mid - 1;
+            }
+            j = lo;
         }
-        int j = lo;
         Rec v = REC[j * G + g];
-        int inext = IB[(j + 1) * G + g];
+        int inext;
+        [[maybe_unused]] double hx = 0, hy = 0;
         [[maybe_unused]] float f1x = 0, f2x = 0, f3x = 0, fhx = 0, f1y = 0, f2y = 0, f3y = 0, fhy = 0;
         auto narrow = [&]() {
+            if constexpr (PACKED) {
+                inext = v.inext;
+                hx = 0.5 * v.c3x; hy = 0.5 * v.c3y;
+            } else {
+                inext = IB[(j + 1) * G + g];
+                if constexpr (!FIT) { hx = v.hx; hy = v.hy; }
+            }
             if constexpr (F32K) {
-                f1x = (float)v.c1x; f2x = (float)v.c2x; f3x = (float)v.c3x; fhx = (float)v.hx;
-                f1y = (float)v.c1y; f2y = (float)v.c2y; f3y = (float)v.c3y; fhy = (float)v.hy;
+                f1x = (float)v.c1x; f2x = (float)v.c2x; f3x = (float)v.c3x; fhx = (float)hx;
+                f1y = (float)v.c1y; f2y = (float)v.c2y; f3y = (float)v.c3y; fhy = (float)hy;
             }
         };
         narrow();
@@ -378,7 +449,6 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a, FitArgs fa)
             while (q >= inext) {
                 ++j;
                 v = REC[j * G + g];
-                inext = IB[(j + 1) * G + g];
                 narrow();
             }
             const double s = (double)q * step;
@@ -399,8 +469,8 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a, FitArgs fa)
                 // |x'y'' - y'x''| / (x'^2 + y'^2)^(3/2)   (path.py:58,61), Horner form, explicit FMAs
                 const double t = s - v.u;
                 const double ddx = fma(v.c3x, t, v.c2x), ddy = fma(v.c3y, t, v.c2y);
-                const double dx = fma(t, fma(v.hx, t, v.c2x), v.c1x);
-                const double dy = fma(t, fma(v.hy, t, v.c2y), v.c1y);
+                const double dx = fma(t, fma(hx, t, v.c2x), v.c1x);
+                const double dy = fma(t, fma(hy, t, v.c2y), v.c1y);
                 const double cross = fabs(fma(dx, ddy, -(dy * ddx)));
                 const double n2 = fma(dx, dx, dy * dy);
                 k = ddiv<false>(cross, n2 * dsqrt<false>(n2));
@@ -409,7 +479,7 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a, FitArgs fa)
             if (!STAGED && ++q == n) {  // wrap: back to the first interval
                 q = 0; j = 0;
                 v = REC[g];
-                inext = IB[G + g];
+                narrow();
             }
             if (STAGED) ++q;
         }
@@ -420,6 +490,7 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a, FitArgs fa)
         if constexpr (STAGED) KT[(size_t)q * G + g] = k;
         if (k > best) { best = k; bi = q; }
     });
+    K1B_STAMP(3);
     // first maximum of the curvature == a minimum of v_local (velocity.py:34).  Lanes l, l+G, l+2G, ...
     // hold consecutive chunks of one candidate: fold the upper lanes into the lower ones, lower chunk first
 #pragma unroll
@@ -442,12 +513,31 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a, FitArgs fa)
         a.len[b0 + tid] = LEN[tid];
     }
     __syncthreads();
+    K1B_STAMP(4);
     // ---- W: write-out, rotated: row i of candidate g is sample (i + rot_g) mod n ----------------------------
     {
         const int q0 = ROT[g];
         double* dst = a.kap + tile_base(b0 + g, n);
         float* dst32 = a.kap32 ? a.kap32 + tile_base(b0 + g, n) : nullptr;
-        if constexpr (STAGED) {
+        if constexpr (STAGED && K1B_WLIN) {
+            // rotated row i = c, c + CPT, ... takes tile row i + q0 (- n past the wrap): the four candidates of a row
+            // segment stay in the same iteration (one full 32-byte sector per store), the source cursor steps back
+            // by n rows once; the fp32 copy has its own loop (no predicated-off stores in the fp64 one)
+            const double* src = KT + (size_t)(c + q0) * G + g;
+            const int iw = n - q0;  // first rotated row past the wrap
+            if (F32K || dst32) {
+                for (int i = c; i < n; i += CPT) {
+                    const double k = src[(size_t)(i - c) * G - ((i >= iw) ? (size_t)n * G : 0)];
+                    if (!F32K) dst[(size_t)i * TILE] = k;
+                    dst32[(size_t)i * TILE] = (float)k;
+                }
+            } else {
+                double* d = dst + (size_t)c * TILE;
+#pragma unroll 4
+                for (int i = c; i < n; i += CPT, d += (size_t)CPT * TILE)
+                    *d = src[(i - c) * G - ((i >= iw) ? n * G : 0)];
+            }
+        } else if constexpr (STAGED) {
             for (int i = c; i < n; i += CPT) {
                 int q = i + q0;
                 q = (q >= n) ? q - n : q;
@@ -465,6 +555,7 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a, FitArgs fa)
             });
         }
     }
+    K1B_STAMP(5);
 }
 
 }  // namespace ltk

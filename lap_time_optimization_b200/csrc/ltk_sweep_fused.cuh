@@ -40,6 +40,13 @@ constexpr size_t SWEEP_SLACK = 1024;
 #ifndef LTK_SWEEP_PREFETCH
 #define LTK_SWEEP_PREFETCH 2  // blocks of FUSED_UNROLL rows fetched into L1 ahead of the register look-ahead (0: none)
 #endif
+#ifndef LTK_SWEEP_LOOKAHEAD
+#define LTK_SWEEP_LOOKAHEAD 1  // 1: the next block's rows are loaded into registers while the current block runs;
+#endif                         // 0: every block loads its own rows (L1 hits behind the prefetch), no look-ahead registers
+#ifndef LTK_SWEEP_MINB
+#define LTK_SWEEP_MINB 8       // resident CTAs per SM the register budget is cut for
+#endif
+constexpr int SWEEP_LA = LTK_SWEEP_LOOKAHEAD ? 1 : 0;
 static_assert(SWEEP_SLACK >= (2 + LTK_SWEEP_PREFETCH) * FUSED_UNROLL * TILE * sizeof(double),
               "look-ahead rows must fit the slack");
 
@@ -64,6 +71,7 @@ struct FusedArgs {
     int ns;
     long long B, Bp;
     long long first, last;  // candidates [first, last) of the padded population are this launch's (multiples of 32)
+    TopkFuse tk;            // tk.k > 0: the CTAs select the population's k best in their epilogue (ltk_topk_fused.cuh)
 };
 
 // ---- engine map by cell table ---------------------------------------------------------------------
@@ -233,27 +241,14 @@ __device__ __forceinline__ void fused_block(const VehDev& V, const FusedShared& 
     }
 }
 
+// the two sweeps of candidate b (every lane of the warp is inside the padded population); returns the lap time
 template <int KIND, int ENG>
-__global__ void __launch_bounds__(FUSED_THREADS, 8) k23_sweep(FusedArgs a, VehDev V)
+__device__ __forceinline__ double k23_candidate(const FusedArgs& a, const VehDev& V, const FusedShared& S,
+                                                const EngineTable& T, const long long b)
 {
     constexpr int U = FUSED_UNROLL;
     constexpr size_t P = TILE;  // row pitch in doubles
     constexpr int NPAD = (ENG == 16) ? 16 : 8;  // comparison count of the library-operator path
-    __shared__ FusedShared S;
-    __shared__ EngineTable T;  // library-operator path (tails, irregular blocks, dumps)
-    if (KIND == 0) {
-        load_engine_table(T, V, threadIdx.x, FUSED_THREADS);
-        for (int i = threadIdx.x; i <= LTK_MAX_ENGINE_MAP; i += FUSED_THREADS) {
-            S.seg[i].s = V.ext_s[i]; S.seg[i].b = V.ext_b[i]; S.seg[i].f = V.ext_f[i]; S.seg[i].pad = 0.0;
-        }
-        if (ENG == 0)
-            for (int i = threadIdx.x; i <= V.lut_top; i += FUSED_THREADS) S.cell[i] = a.lut[i];
-        __syncthreads();
-    }
-    const long long b_raw = a.first + (long long)blockIdx.x * FUSED_THREADS + threadIdx.x;
-    if (b_raw - (threadIdx.x & 31) >= a.last) return;  // whole warp beyond this launch's candidates
-    // lanes in [B, Bp) sweep the padding copies K1 wrote (so that warp votes see a full warp)
-    const long long b = b_raw;
     const int n = a.ns - 1;
     const size_t base = tile_base(b, n);
     const int p = a.rot[b];
@@ -336,19 +331,32 @@ __global__ void __launch_bounds__(FUSED_THREADS, 8) k23_sweep(FusedArgs a, VehDe
     int t = 0;  // steps done in this phase
     if (!dump) {
         double fc[U], fn[U], bc[U], bn[U];
+        if (SWEEP_LA) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) {  // look-ahead loads are unconditional: see SWEEP_SLACK
-            fc[u] = kfp[(size_t)u * P];
-            bc[u] = *(kbp - (size_t)u * P);
+            for (int u = 0; u < U; ++u) {  // look-ahead loads are unconditional: see SWEEP_SLACK
+                fc[u] = kfp[(size_t)u * P];
+                bc[u] = *(kbp - (size_t)u * P);
+            }
+        } else if (LTK_SWEEP_PREFETCH) {  // the first blocks' lines
+#pragma unroll
+            for (int u = 0; u < LTK_SWEEP_PREFETCH * U; ++u) {
+                prefetch_l1(kfp + (size_t)u * P);
+                prefetch_l1(kbp - (size_t)u * P);
+            }
         }
         for (; t + U <= h; t += U) {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                fn[u] = kfp[(size_t)(U + u) * P];
-                bn[u] = *(kbp - (size_t)(U + u) * P);
+                if (SWEEP_LA) {
+                    fn[u] = kfp[(size_t)(U + u) * P];
+                    bn[u] = *(kbp - (size_t)(U + u) * P);
+                } else {
+                    fc[u] = kfp[(size_t)u * P];
+                    bc[u] = *(kbp - (size_t)u * P);
+                }
                 if (LTK_SWEEP_PREFETCH) {
-                    prefetch_l1(kfp + (size_t)((1 + LTK_SWEEP_PREFETCH) * U + u) * P);
-                    prefetch_l1(kbp - (size_t)((1 + LTK_SWEEP_PREFETCH) * U + u) * P);
+                    prefetch_l1(kfp + (size_t)((SWEEP_LA + LTK_SWEEP_PREFETCH) * U + u) * P);
+                    prefetch_l1(kbp - (size_t)((SWEEP_LA + LTK_SWEEP_PREFETCH) * U + u) * P);
                 }
             }
             bool regular = state_ok;
@@ -366,8 +374,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, 8) k23_sweep(FusedArgs a, VehDe
                 for (int u = 0; u < U; ++u) step_safe(1);
                 state_ok = chains_regular();
             }
+            if (SWEEP_LA) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) { fc[u] = fn[u]; bc[u] = bn[u]; }
+                for (int u = 0; u < U; ++u) { fc[u] = fn[u]; bc[u] = bn[u]; }
+            }
         }
     }
 #pragma unroll 1
@@ -395,25 +405,42 @@ __global__ void __launch_bounds__(FUSED_THREADS, 8) k23_sweep(FusedArgs a, VehDe
     t = 0;
     if (!dump) {
         double fc[U], fn[U], bc[U], bn[U], fo[U], fon[U], bo[U], bon[U];
+        if (SWEEP_LA) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            fc[u] = kfp[(size_t)u * P];
-            fo[u] = sfp[(size_t)u * P];
-            bc[u] = *(kbp - (size_t)u * P);
-            bo[u] = *(sbp - (size_t)u * P);
+            for (int u = 0; u < U; ++u) {
+                fc[u] = kfp[(size_t)u * P];
+                fo[u] = sfp[(size_t)u * P];
+                bc[u] = *(kbp - (size_t)u * P);
+                bo[u] = *(sbp - (size_t)u * P);
+            }
+        } else if (LTK_SWEEP_PREFETCH) {
+#pragma unroll
+            for (int u = 0; u < LTK_SWEEP_PREFETCH * U; ++u) {
+                prefetch_l1(kfp + (size_t)u * P);
+                prefetch_l1(sfp + (size_t)u * P);
+                prefetch_l1(kbp - (size_t)u * P);
+                prefetch_l1(sbp - (size_t)u * P);
+            }
         }
         for (; t + U <= h; t += U) {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                fn[u] = kfp[(size_t)(U + u) * P];
-                fon[u] = sfp[(size_t)(U + u) * P];
-                bn[u] = *(kbp - (size_t)(U + u) * P);
-                bon[u] = *(sbp - (size_t)(U + u) * P);
+                if (SWEEP_LA) {
+                    fn[u] = kfp[(size_t)(U + u) * P];
+                    fon[u] = sfp[(size_t)(U + u) * P];
+                    bn[u] = *(kbp - (size_t)(U + u) * P);
+                    bon[u] = *(sbp - (size_t)(U + u) * P);
+                } else {
+                    fc[u] = kfp[(size_t)u * P];
+                    fo[u] = sfp[(size_t)u * P];
+                    bc[u] = *(kbp - (size_t)u * P);
+                    bo[u] = *(sbp - (size_t)u * P);
+                }
                 if (LTK_SWEEP_PREFETCH) {
-                    prefetch_l1(kfp + (size_t)((1 + LTK_SWEEP_PREFETCH) * U + u) * P);
-                    prefetch_l1(sfp + (size_t)((1 + LTK_SWEEP_PREFETCH) * U + u) * P);
-                    prefetch_l1(kbp - (size_t)((1 + LTK_SWEEP_PREFETCH) * U + u) * P);
-                    prefetch_l1(sbp - (size_t)((1 + LTK_SWEEP_PREFETCH) * U + u) * P);
+                    prefetch_l1(kfp + (size_t)((SWEEP_LA + LTK_SWEEP_PREFETCH) * U + u) * P);
+                    prefetch_l1(sfp + (size_t)((SWEEP_LA + LTK_SWEEP_PREFETCH) * U + u) * P);
+                    prefetch_l1(kbp - (size_t)((SWEEP_LA + LTK_SWEEP_PREFETCH) * U + u) * P);
+                    prefetch_l1(sbp - (size_t)((SWEEP_LA + LTK_SWEEP_PREFETCH) * U + u) * P);
                 }
             }
             bool regular = state_ok;
@@ -432,8 +459,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, 8) k23_sweep(FusedArgs a, VehDe
                 for (int u = 0; u < U; ++u) step_safe(2);
                 state_ok = chains_regular();
             }
+            if (SWEEP_LA) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) { fc[u] = fn[u]; bc[u] = bn[u]; fo[u] = fon[u]; bo[u] = bon[u]; }
+                for (int u = 0; u < U; ++u) { fc[u] = fn[u]; bc[u] = bn[u]; fo[u] = fon[u]; bo[u] = bon[u]; }
+            }
         }
     }
 #pragma unroll 1
@@ -443,7 +472,33 @@ __global__ void __launch_bounds__(FUSED_THREADS, 8) k23_sweep(FusedArgs a, VehDe
 #undef LTK_RB
     double lap = c.lap_f + c.lap_b;
     if (has_mid) lap = lap + term_mid;
-    if (b < a.B) a.lap[b] = lap + term0;
+    return lap + term0;
+}
+
+template <int KIND, int ENG>
+__global__ void __launch_bounds__(FUSED_THREADS, LTK_SWEEP_MINB) k23_sweep(FusedArgs a, VehDev V)
+{
+    __shared__ FusedShared S;
+    __shared__ EngineTable T;  // library-operator path (tails, irregular blocks, dumps)
+    if (KIND == 0) {
+        load_engine_table(T, V, threadIdx.x, FUSED_THREADS);
+        for (int i = threadIdx.x; i <= LTK_MAX_ENGINE_MAP; i += FUSED_THREADS) {
+            S.seg[i].s = V.ext_s[i]; S.seg[i].b = V.ext_b[i]; S.seg[i].f = V.ext_f[i]; S.seg[i].pad = 0.0;
+        }
+        if (ENG == 0)
+            for (int i = threadIdx.x; i <= V.lut_top; i += FUSED_THREADS) S.cell[i] = a.lut[i];
+        __syncthreads();
+    }
+    const long long b = a.first + (long long)blockIdx.x * FUSED_THREADS + threadIdx.x;
+    // a whole warp beyond this launch's candidates has nothing to sweep; lanes in [B, Bp) sweep the padding copies
+    // K1 wrote (so that warp votes see a full warp)
+    const bool live = b - (threadIdx.x & 31) < a.last;
+    double lap = 0.0;
+    if (live) {
+        lap = k23_candidate<KIND, ENG>(a, V, S, T, b);
+        if (b < a.B) a.lap[b] = lap;
+    }
+    if (a.tk.k > 0) topk_epilogue(a.tk, live && b < a.B, lap, b);
 }
 
 }  // namespace ltk

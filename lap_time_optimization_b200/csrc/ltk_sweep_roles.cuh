@@ -267,11 +267,14 @@ __global__ void __launch_bounds__(ROLES_THREADS, 14) k23_roles(FusedArgs a, VehD
 
     if (role == 1) { x_lap[lane] = c.lap; x_mid[lane] = term_mid; }
     __syncthreads();
-    if (role == 0 && b < a.B) {
-        double lap = c.lap + x_lap[lane];
+    double lap = 0.0;
+    if (role == 0) {
+        lap = c.lap + x_lap[lane];
         if (has_mid) lap = lap + x_mid[lane];
-        a.lap[b] = lap + term0;
+        lap = lap + term0;
+        if (b < a.B) a.lap[b] = lap;
     }
+    if (a.tk.k > 0) topk_epilogue(a.tk, role == 0 && b < a.B, lap, b);
 }
 
 }  // namespace ltk

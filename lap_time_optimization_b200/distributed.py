@@ -50,7 +50,6 @@ def allgather_topk(local_laps, local_idx, k, group=None, merge=merge_topk):
 def sharded_population_topk(evaluator, local_alphas, index_base, k, group=None):
     """Score this rank's shard on its GPU, local top-k with global indices, all-gather, merge.
     Returns (local_laps [B_local] CUDA, best_laps[k], best_idx[k])."""
-    d_lap = evaluator.lap_times_device(local_alphas)
-    best, idx = evaluator.topk_device(d_lap, k, index_base=index_base)
+    d_lap, best, idx = evaluator.lap_times_topk_device(local_alphas, k=k, index_base=index_base)
     g_best, g_idx = allgather_topk(best, idx, k, group, merge=evaluator.merge_topk_device)
     return d_lap, g_best, g_idx

@@ -441,8 +441,8 @@ class LapTimeEvaluator:
                 lane.stream.wait_event(sl["ev_in"])
                 if sl["used"]:
                     lane.stream.wait_event(sl["ev_out"])  # d_lap of this slot has been read back
-                d_lap = lane.ev.lap_times_device(sl["d_in"][:B], out=sl["d_lap"][:B], _lane=len(pool) > 1)
-                best, idx = lane.ev.topk_device(d_lap, k, index_base=base)
+                d_lap, best, idx = lane.ev.lap_times_topk_device(sl["d_in"][:B], out=sl["d_lap"][:B], k=k,
+                                                                 index_base=base, _lane=len(pool) > 1)
                 sl["ev_done"].record(lane.stream)
             if finish is not None:
                 best, idx = self._finish_async(finish, best, idx, sl["ev_done"])
@@ -475,8 +475,8 @@ class LapTimeEvaluator:
         for i, pop in enumerate(populations):
             lane = pool[i % len(pool)]
             with torch.cuda.stream(lane.stream):
-                d_lap = lane.ev.lap_times_device(pop, out=outs[i % len(pool)], _lane=len(pool) > 1)
-                last = lane.ev.topk_device(d_lap, k, index_base=index_base)
+                last = lane.ev.lap_times_topk_device(pop, out=outs[i % len(pool)], k=k, index_base=index_base,
+                                                     _lane=len(pool) > 1)[1:]
                 if finish is not None:
                     done = torch.cuda.Event()
                     done.record(lane.stream)
@@ -503,6 +503,31 @@ class LapTimeEvaluator:
             out = finish(best, idx)
             ready.record(comm)
         return out
+
+    def lap_times_topk_device(self, alphas, out=None, k=DEFAULT_TOPK, index_base=0, _lane=False):
+        """`lap_times_device` and `topk_device` of the same population in one call: -> (laps[B], best[k], idx[k])
+        CUDA tensors.  A population that fits one chunk goes through `ltk_eval_alphas_topk` -- the k best are
+        selected in the sweep kernel's epilogue, no separate selection launch; anything else (multi-wave
+        populations, chunked workspaces) scores first and selects afterwards.  Asynchronous on the current stream."""
+        torch = self.torch
+        B = alphas.shape[0]
+        if (alphas.dtype != torch.float64 or not alphas.is_cuda or alphas.dim() != 2 or alphas.shape[1] != self.n_alpha
+                or not alphas.is_contiguous() or B < 1 or (B >= 2 * self.WAVE and self.wave_lanes > 1)
+                or B > self.max_batch()):
+            laps = self.lap_times_device(alphas, out=out, _lane=_lane)
+            return (laps,) + tuple(self.topk_device(laps, k, index_base=index_base))
+        if out is None:
+            out = torch.empty(B, dtype=torch.float64, device=self.device)
+        if not _lane:
+            self._set_split(True)
+        best = torch.empty(k, dtype=torch.float64, device=self.device)
+        idx = torch.empty(k, dtype=torch.int64, device=self.device)
+        ws = self._workspace(B)
+        rc = self.lib.ltk_eval_alphas_topk(self._ctx, _device.ptr(alphas), B, _device.ptr(out), _device.ptr(ws),
+                                           ws.numel(), int(index_base), int(k), _device.ptr(best), _device.ptr(idx),
+                                           _device.stream_ptr(torch, self.device))
+        _native.check(rc, self._ctx)
+        return out, best, idx
 
     def topk_device(self, laps, k=DEFAULT_TOPK, index_base=0):
         """Stable ascending top-k of a CUDA lap tensor -> (lap[k], idx[k]) CUDA tensors."""

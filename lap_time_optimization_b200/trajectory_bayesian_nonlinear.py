@@ -111,8 +111,7 @@ class TrajectoryBayesianNonlinear:
         (alphas[count, n_alpha], laps[count], best_laps[k], best_idx[k])."""
         ev = self.evaluator
         d_a = self.random_population_device(count, key)
-        d_lap = ev.lap_times_device(d_a)
-        best, idx = ev.topk_device(d_lap, k)
+        d_lap, best, idx = ev.lap_times_topk_device(d_a, k=k)
         return d_a, d_lap, best, idx
 
     def population_topk(self, alphas, k=DEFAULT_TOPK):
@@ -120,8 +119,7 @@ class TrajectoryBayesianNonlinear:
         (tbn.py:253-257).  Returns (laps[B], best_laps[k], best_indices[k]) as numpy arrays."""
         ev = self.evaluator
         d_a = alphas if hasattr(alphas, "is_cuda") else _device.to_device(alphas, ev.device)
-        d_lap = ev.lap_times_device(d_a)
-        best, idx = ev.topk_device(d_lap, k)
+        d_lap, best, idx = ev.lap_times_topk_device(d_a, k=k)
         return d_lap.cpu().numpy(), best.cpu().numpy(), idx.cpu().numpy()
 
     # -- the --nonlinear stage: random population -> k best -> COBYLA from each (tbn.py:207-270) -------

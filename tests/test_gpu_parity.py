@@ -405,6 +405,57 @@ def test_topk_ties_nan_and_short_input(buckmore):
     assert np.array_equal(idx, o_idx) and np.array_equal(best, o_best)
 
 
+@pytest.mark.parametrize("B,k", [(1, 3), (31, 10), (1000, 10), (20000, 1), (28417, 16), (40000, 10), (65536, 10),
+                                 (65536, 17), (70001, 10)])
+def test_topk_fused_into_sweep_epilogue(buckmore, B, k):
+    """ltk_eval_alphas_topk (selection in the sweep CTAs' epilogue: one-chain kernel, two-chain kernel, the split
+    over both, ragged tails, the k > 16 fallback) against the separate launch and a stable host sort; duplicated
+    candidates make ties that must resolve to the lower index; repeated calls check the tickets return to zero."""
+    ev, _ = buckmore
+    rng = np.random.default_rng(B + k)
+    a = rng.uniform(0.0, 0.99, (B, ev.n_alpha))
+    if B >= 1000:
+        a[B // 2:B // 2 + 40] = a[3:43]  # ties between distant CTAs
+        a[-1] = a[0]
+    d_a = torch.as_tensor(a).cuda()
+    ev._set_split(True)
+    for rep in range(3):
+        laps, best, idx = ev.lap_times_topk_device(d_a, k=k, index_base=1000)
+        laps2 = ev.lap_times_device(d_a)
+        best2, idx2 = ev.topk_device(laps2, k, index_base=1000)
+        assert torch.equal(laps, laps2)
+        assert torch.equal(idx, idx2) and torch.equal(best, best2), (rep, idx.tolist(), idx2.tolist())
+    h = laps.cpu().numpy()
+    order = np.argsort(h, kind="stable")[:k]
+    n = min(k, B)
+    assert np.array_equal(idx.cpu().numpy()[:n], order[:n] + 1000) and np.array_equal(best.cpu().numpy()[:n], h[order[:n]])
+    if B < k:
+        assert (idx.cpu().numpy()[B:] == -1).all() and np.isinf(best.cpu().numpy()[B:]).all()
+
+
+def test_topk_fused_with_lanes_and_nan(buckmore):
+    """The fused selection on three lanes (one sweep launch per population, contexts of their own) and with NaN lap
+    times in the population (NaN sorts last, as in ltk_topk)."""
+    ev, _ = buckmore
+    rng = np.random.default_rng(77)
+    pops = [torch.as_tensor(rng.uniform(0.0, 0.99, (4096 + 32 * i, ev.n_alpha))).cuda() for i in range(6)]
+    pops[2][5, :] = float("nan")
+    pops[2][4000, 3] = float("nan")
+    outs = [torch.empty(4096 + 32 * 5, dtype=torch.float64, device="cuda") for _ in range(3)]
+    got = []
+    for i, p in enumerate(pops):  # one at a time through run_resident so that every result can be read back
+        best, idx = ev.run_resident([p], [outs[0][:p.shape[0]]], 10, index_base=7, lanes=3)
+        torch.cuda.synchronize()
+        got.append((best.cpu().numpy(), idx.cpu().numpy(), outs[0][:p.shape[0]].cpu().numpy().copy()))
+    last = ev.run_resident(pops, [o for o in outs], 10, index_base=7, lanes=3)
+    torch.cuda.synchronize()
+    for (best, idx, h), p in zip(got, pops):
+        key = np.where(np.isnan(h), np.inf, h)
+        order = np.argsort(key, kind="stable")[:10]
+        assert np.array_equal(idx, order + 7) and np.array_equal(best, key[order])
+    assert np.array_equal(last[1].cpu().numpy(), got[-1][1])
+
+
 def test_merge_pairs_kernel(buckmore):
     ev, _ = buckmore
     laps = torch.tensor([2.0, 1.0, 1.0, float("nan"), 3.0, 0.5, 9.0], dtype=torch.float64, device="cuda")
