@@ -6,7 +6,8 @@
 
 A "step" scores one population of `--candidates` (default 65,536 = BASELINE.json configs[1]) random
 alpha vectors per GPU: K1a spline solve -> K1b curvature (rotated write-out) -> K23 forward + backward
-sweeps with the lap sum -> top-10 (-> one all-gather of 160 B/rank + merge when N > 1).  Candidates are
+sweeps with the lap sum and the top-10 selected in the sweep's epilogue -- three kernel launches, one
+ltk_eval_alphas_topk call (-> one all-gather of 160 B/rank + merge when N > 1).  Candidates are
 independent, so ranks get disjoint populations and the scaling is weak.  `--lanes` (default 3) steps are
 in flight at a time, each on its own stream (LapTimeEvaluator.lanes).  Prints ONE JSON line (rank 0).
 
@@ -419,16 +420,17 @@ def run_config(D, ltk, local, tag, vehicle, ns, total, key, timed_generation, pe
     return res
 
 
-def h2d_probe(D, nbytes, reps=24):
+def h2d_probe(D, nbytes, reps=96, warm=32):
     """Pinned host -> device bandwidth of every rank while ALL ranks copy at the same time (the e2e path's
-    upload of one population, back to back)."""
+    upload of one population, back to back).  The link needs ~0.5 GB of traffic to reach its steady rate (measured
+    on the pool's boxes: 18 GB/s over the first 24 copies of 22.5 MB, 24-36 GB/s over 100), hence the long warm-up."""
     torch = D.torch
     h = torch.empty(nbytes // 8, dtype=torch.float64).pin_memory()
     d = torch.empty(nbytes // 8, dtype=torch.float64, device=D.dev)
     st = torch.cuda.Stream(D.dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(st):
-        for _ in range(3):
+        for _ in range(warm):
             d.copy_(h, non_blocking=True)
     D.barrier()
     with torch.cuda.stream(st):
