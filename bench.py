@@ -263,6 +263,21 @@ def fp64_pipe_model(args, B, n, ms_per_step, clocks):
             "peak": "64 DFMA/clk/SM measured (tools/ubench/fp64_lat.cu): 37.2 TFLOP/s at 1965 MHz"}
 
 
+def issue_model(args, B, n, ms_per_step, clocks):
+    """Issue-slot occupancy of one step under the cost model of DESIGN.md section 3 ("What binds"): one cycle per
+    instruction, two per FP64 instruction, three per DFMA with three distinct register operands (tools/ubench), applied
+    to the SASS instruction counts of the kernels' loops.  Cycles per sample and warp: K23 277 (a block of two row pairs =
+    319 instructions, 160 FP64, 76 three-operand DFMAs = 555 cycles), K1b 135 (sample loop 88, interval switches 7,
+    write-out 10, per-CTA phases 30), K1a 20.  fp64 sweeps only; this is the builder's model, not a counter."""
+    if args.sweep_bits != 64 or args.spline != "tridiagonal":
+        return None
+    per_sample = 277 + 135 + 20
+    mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    need = B * n * per_sample / 32.0 / (148 * 4)
+    have = ms_per_step * 1e-3 * mhz * 1e6
+    return {"model_cycles_per_sample_and_warp": per_sample, "frac": need / have, "sm_mhz": mhz}
+
+
 def _numpy_simd():
     try:
         from numpy._core._multiarray_umath import __cpu_features__ as feats
@@ -530,10 +545,11 @@ def run_ours(args):
     #      buffers: the H2D copy of step i+1 and the D2H of step i-1 overlap the kernels of step i; every
     #      byte of every step still crosses PCIe inside the timed region. ------------------------------
     pin_in = [torch.as_tensor(h).pin_memory() for h in host_sets[:4]]
+    e2e_finish = None if os.environ.get("LTK_BENCH_E2E_NO_FINISH") else finish  # diagnostic: e2e without the all-gather
     def e2e_run(nsteps):
         checksum = 0.0
         for laps, best_h, idx_h in ev.stream_populations((pin_in[i % 4] for i in range(nsteps)), TOPK,
-                                                         index_base=base, index_stride=0, finish=finish,
+                                                         index_base=base, index_stride=0, finish=e2e_finish,
                                                          lanes=LANES, slots=args.e2e_slots):
             checksum += float(best_h[0]) + float(laps[-1])  # results are consumed on the host
         return checksum
@@ -639,7 +655,7 @@ def run_ours(args):
             "gpu_launches": launches,
             # `bound`: the contract's roof for this byte-moving path is HBM and `frac` is measured against it; what
             # actually limits the kernel is named in `binding` (FP64 issue + dependent-chain latency)
-            "roofline": {"bound": "hbm", "binding": "fp64_pipe/latency", "kernel": dom, "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "binding": "fp64_issue", "kernel": dom, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_commit": traffic_commit,
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_candidate": alg[dom],
@@ -648,6 +664,7 @@ def run_ours(args):
                          # sample from the SASS instruction counts and the measured issue costs (tools/ubench:
                          # 2 cycles per FP64 warp instruction and scheduler, 3 for a three-register DFMA)
                          "fp64_pipe": fp64_pipe_model(args, B, n, ms_total / args.steps, clocks),
+                         "issue_model": issue_model(args, B, n, ms_total / args.steps, clocks),
                          "pipeline": {"bytes_per_candidate": a_staged,
                                       "achieved": a_staged * B * world / (ms_total / args.steps * 1e-3) / 1e9 / world,
                                       "frac": a_staged * B / (ms_total / args.steps * 1e-3) / 1e9 / peak}},

@@ -6,6 +6,7 @@ through pinned memory).  Everything numeric happens in libltk's kernels."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 import math
 
 import numpy as np
@@ -384,12 +385,16 @@ class LapTimeEvaluator:
         # would queue behind the download of the previous one, which waits for that one's kernels
         if getattr(self, "_copy_streams", None) is None:
             self._copy_streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+            # LTK_E2E_COPY_STREAMS=2 (A/B): uploads alternate between two streams, two host->device copies in flight
+            self._copy_in_extra = [torch.cuda.Stream(dev)
+                                   for _ in range(max(0, int(os.environ.get("LTK_E2E_COPY_STREAMS", "1")) - 1))]
         copy_in, copy_out = self._copy_streams
+        copy_ins = [copy_in] + self._copy_in_extra
         # join the caller's stream: lane 0 is this evaluator (its workspace, top-k scratch and ticket), and
         # earlier asynchronous calls on the current stream may still be using them
         entry = torch.cuda.Event()
         entry.record(torch.cuda.current_stream(dev))
-        for st_ in [lane.stream for lane in pool] + [copy_in, copy_out]:
+        for st_ in [lane.stream for lane in pool] + copy_ins + [copy_out]:
             st_.wait_event(entry)
         nslot = max(len(pool), int(slots) if slots else 2 * len(pool))
         slots = [None] * nslot
@@ -432,11 +437,12 @@ class LapTimeEvaluator:
                     sl["ev_in"].synchronize()  # the previous H2D out of this staging buffer
                 sl["h_stage"][:B].copy_(t)
                 t = sl["h_stage"][:B]
-            with torch.cuda.stream(copy_in):
+            cin = copy_ins[i % len(copy_ins)]
+            with torch.cuda.stream(cin):
                 if sl["used"]:
-                    copy_in.wait_event(sl["ev_done"])  # kernels that read d_in of this slot
+                    cin.wait_event(sl["ev_done"])  # kernels that read d_in of this slot
                 sl["d_in"][:B].copy_(t, non_blocking=True)
-                sl["ev_in"].record(copy_in)
+                sl["ev_in"].record(cin)
             with torch.cuda.stream(lane.stream):
                 lane.stream.wait_event(sl["ev_in"])
                 if sl["used"]:
