@@ -554,7 +554,9 @@ def run_ours(args):
             checksum += float(best_h[0]) + float(laps[-1])  # results are consumed on the host
         return checksum
 
-    e2e_run(max(3, (args.e2e_slots or 2 * LANES) + 1))  # every buffer set exists before the timed region
+    # every buffer set exists before the timed region, and the host link is at its steady rate (it needs ~0.5 GB of
+    # traffic to get there: 18 GB/s over the first 24 uploads of a cold link, 53 GB/s after 32; profiles/README.md)
+    e2e_run(max(32, (args.e2e_slots or 2 * LANES) + 1))
     barrier()
     t0e = time.perf_counter()
     e2e_run(args.steps)
