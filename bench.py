@@ -113,6 +113,17 @@ def cpu_rate(args, sample, processes):
     return sample / dt, laps, a
 
 
+def port_laps_baseline_dispatch(args, a):
+    """The reference-equivalent port on the same rows with numpy's AVX512 dispatch switched off (a process of its own).
+    The unmodified reference evaluates `(dx**2 + dy**2) ** 1.5` (path.py:58) with numpy's vendored SVML `pow` on AVX512
+    hosts and with libm's elsewhere, and its TBR18 lap times move by up to 6.5e-9 between the two
+    (profiles/README.md): parity is reported against both."""
+    from oracle.reference_port import lap_times_baseline_dispatch
+
+    tj, vj = data_paths(args.vehicle)
+    return lap_times_baseline_dispatch(tj, WIDTH, vj, a, "bayes", args.ns)
+
+
 def rel_stats(ours, ref):
     rel = np.abs(np.asarray(ours) - np.asarray(ref)) / np.abs(ref)
     return {"n": int(rel.size), "median": float(np.median(rel)), "p99": float(np.percentile(rel, 99)),
@@ -475,9 +486,14 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     cpu_result = None
+    cpu_laps_base = None
     if world == 1 and not args.no_cpu_baseline:
         # the CPU baseline forks a worker pool: do it before this process owns a CUDA context
         cpu_result = cpu_rate(args, args.cpu_sample, os.cpu_count() or 1)
+        try:
+            cpu_laps_base = port_laps_baseline_dispatch(args, cpu_result[2])
+        except Exception:  # the probe is extra evidence, not part of the contract
+            cpu_laps_base = None
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -585,7 +601,13 @@ def run_ours(args):
             g = ev.lap_times(cpu_a)
             st_ = rel_stats(g, cpu_laps)
             st_["top10_identical"] = bool(np.array_equal(stable_topk(g, TOPK)[0], stable_topk(cpu_laps, TOPK)[0]))
+            if cpu_laps_base is not None:  # the same rows against the reference's arithmetic on non-AVX512 hosts
+                st_["vs_numpy_baseline_dispatch"] = rel_stats(g, cpu_laps_base)
             parity[mode] = st_
+        if cpu_laps_base is not None:
+            parity["reference_against_itself"] = dict(
+                rel_stats(cpu_laps, cpu_laps_base),
+                what="the port under numpy's dispatch on this host against the port under numpy's baseline dispatch (libm pow)")
         ev.set_spline_mode(args.spline)
     # ---- variants: FITPACK spline mode, fp32 sweeps -------------------------------------------------------
     variants = None

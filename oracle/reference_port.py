@@ -316,3 +316,34 @@ def lap_times_pool(track_json, width, vehicle_json, alphas, mode="bayes", ns=Non
         return pool.lap_times(alphas)
     finally:
         pool.close()
+
+
+# numpy dispatches `x ** 1.5` (path.py:58) to its vendored SVML `pow` on AVX512 hosts and to libm's elsewhere; the two
+# differ by 1 ulp in ~5 % of the arguments and the reference's TBR18 lap times move by up to 6.5e-9 between such hosts.
+NUMPY_AVX512_FEATURES = "AVX512F AVX512CD AVX512_SKX AVX512_CLX AVX512_CNL AVX512_ICL AVX512_SPR"
+_SUBPROCESS_SNIPPET = """
+import sys, numpy as np
+sys.path.insert(0, {root!r})
+from oracle.reference_port import lap_times_pool
+np.save({out!r}, lap_times_pool({tj!r}, {width!r}, {vj!r}, np.load({inp!r}), {mode!r}, {ns!r}))
+"""
+
+
+def lap_times_baseline_dispatch(track_json, width, vehicle_json, alphas, mode="bayes", ns=None):
+    """`lap_times_pool` in a process of its own with numpy's AVX512 kernels switched off (NPY_DISABLE_CPU_FEATURES is
+    read when numpy is imported): the reference's arithmetic on a host without AVX512 (libm `pow`)."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.TemporaryDirectory() as d:
+        inp, out = os.path.join(d, "a.npy"), os.path.join(d, "laps.npy")
+        np.save(inp, np.asarray(alphas, dtype=np.float64))
+        code = _SUBPROCESS_SNIPPET.format(root=root, inp=inp, out=out, tj=track_json, width=width, vj=vehicle_json,
+                                          mode=mode, ns=ns)
+        subprocess.run([sys.executable, "-c", code], env=dict(os.environ, NPY_DISABLE_CPU_FEATURES=NUMPY_AVX512_FEATURES),
+                       check=True, capture_output=True)
+        return np.load(out)
+
