@@ -80,12 +80,14 @@ int ltk_set_sweep_precision(ltk_ctx *ctx, int bits);
  *   LTK_SPLINE_TRIDIAGONAL (default): cyclic tridiagonal solve for the second derivatives (Thomas +
  *       Sherman-Morrison), Horner evaluation.  Curvature agrees with SciPy's to ~1e-13 of its maximum; TBR18's
  *       friction-circle cancellation (vehicle.py:29-35) turns that into lap-time differences of median 2e-11,
- *       but > 1e-9 on about one candidate in 4,000.
+ *       but > 1e-9 on about one candidate in 2,400 (27 of 65,536, worst 6.5e-9).
  *   LTK_SPLINE_FITPACK: SciPy FITPACK's own algorithm and operation order -- clocur/fpclos (Givens QR of the
  *       periodic collocation matrix, fpbacp) for splprep(k=3, s=0, per=1), splder/fpbspl for splev(der=1|2):
  *       B-spline coefficients and derivative values bit-equal to SciPy's, curvature with a correctly rounded
- *       x**1.5 (numpy's pow is libm's, or an SVML routine one ulp off on AVX512 hosts).  Lap times then equal
- *       the reference's bit for bit on most candidates and stay within 1e-9 on every one.  Costs ~4 KB more
+ *       x**1.5 (numpy's pow is libm's, or an SVML routine one ulp off on AVX512 hosts -- the reference's own TBR18
+ *       lap times move by up to 6.5e-9 between the two).  Lap times then stay within 1e-9 of the reference's on
+ *       every candidate (measured: 0 of 65,536 beyond it, worst 1.9e-10, median 3e-16, against the reference on
+ *       numpy's baseline dispatch; against an AVX512 host they inherit that host's own distance).  Costs ~4 KB more
  *       workspace per candidate (ask ltk_workspace_bytes AFTER setting the mode) and a slower K1. */
 #define LTK_SPLINE_TRIDIAGONAL 0
 #define LTK_SPLINE_FITPACK 1
