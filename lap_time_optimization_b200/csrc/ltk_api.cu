@@ -470,6 +470,7 @@ int run_pipeline(ltk_ctx* ctx, const double* d_alphas, const double* d_xy, int m
     a.alphas = d_alphas; a.xy = d_xy; a.mode = d_xy ? 1 : 0; a.m = m;
     a.left = ctx->d_left; a.diff = ctx->d_diff; a.N = ctx->N; a.ns = ctx->ns;
     a.B = B; a.Bp = w.Bp;
+    a.mu_g = ctx->veh.mu_g;
     a.kap = reinterpret_cast<double*>(ws + w.kap_off);
     // fp32 sweeps read an fp32 copy of the curvature, kept in the upper half of the staging array (its lower
     // half holds the fp32 parked velocities); only the current K1b writes it

@@ -44,6 +44,10 @@ constexpr bool K1B_TRIM = (LTK_K1B_TRIM & 1) != 0;      // packed record
 constexpr bool K1B_GUESS = (LTK_K1B_TRIM & 2) != 0;     // chunk start interval from a proportional guess
 constexpr bool K1B_WLIN = (LTK_K1B_TRIM & 4) != 0;      // write-out with linear cursors
 constexpr bool K1B_STEP = (LTK_K1B_TRIM & 8) != 0;      // sampling step once per candidate
+#ifndef LTK_K1B_TIES
+#define LTK_K1B_TIES 1  // 0 (A/B only): rotation = first maximum of the curvature, plateaus not re-examined
+#endif
+constexpr bool K1B_TIES = LTK_K1B_TIES != 0;
 
 __host__ __device__ inline int k1_chunk(int n, int cpt)
 {
@@ -64,8 +68,8 @@ __host__ __device__ inline size_t k1f_smem_bytes(int G, int threads, int N, int 
     size_t bytes = (size_t)N * G * (fitpack ? sizeof(fit::FitInterval) : K1B_TRIM ? sizeof(IntervalP) : sizeof(Interval));  // interval records [N][G]
     bytes += (tile > scr ? tile : scr) * sizeof(double);             // curvature tile | scratch
     bytes += (size_t)(N + 1) * G * sizeof(int) + 8;                  // first sample index of each interval (+ alignment)
-    bytes += (size_t)G * (2 * sizeof(double) + sizeof(int));         // length, sampling step, rotation
-    bytes += (size_t)(threads / 32) * G * (sizeof(double) + sizeof(int));  // arg-max partials
+    bytes += (size_t)G * (3 * sizeof(double) + sizeof(int));         // length, sampling step, largest curvature, rotation
+    bytes += (size_t)(threads / 32) * G * (sizeof(double) + 2 * sizeof(int));  // arg-max partials
     return (bytes + 15) / 16 * 16;
 }
 
@@ -241,9 +245,11 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a, FitArgs fa)
     int* IB = reinterpret_cast<int*>(KT + ((STAGED && tile > scr) ? tile : scr));   // [N+1][G]
     double* LEN = reinterpret_cast<double*>(IB + (N + 1) * G + (((N + 1) * G) & 1));
     double* STEP = LEN + G;                                             // [G] np.linspace step (tbn.py:71)
-    double* RV = STEP + G;                                              // [NW][G]
+    double* KTHR = STEP + G;                                            // [G] largest curvature (see the arg-min below)
+    double* RV = KTHR + G;                                              // [NW][G]
     int* RI = reinterpret_cast<int*>(RV + NW * G);                      // [NW][G]
-    int* ROT = RI + NW * G;                                             // [G]
+    int* RH = RI + NW * G;                                              // [NW][G]
+    int* ROT = RH + NW * G;                                             // [G]
     // scratch inside the tile region (dead before the first curvature is stored)
     double* PX = KT;                 // [N][G] control points
     double* PY = PX + NG;
@@ -484,35 +490,78 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a, FitArgs fa)
             if (STAGED) ++q;
         }
     };
+    // The sweeps start at np.argmin(v_local), v_local = sqrt(mu g / k) (velocity.py:28-29, :34, :58): the FIRST sample
+    // whose v_local is minimal.  That is the first maximum of the curvature unless an EARLIER sample, a few ulps
+    // below the maximum, rounds to the same v_local (plateaus: circular arcs, symmetric candidates).  Such a sample
+    // shares the maximum's upper 32 bits (or sits one below), so each partial result carries, next to the first
+    // maximum, the largest upper word seen BEFORE it -- one select per sample -- and a CTA that finds the two words
+    // within one of each other (about one candidate in a thousand on real tracks) looks again, exactly.
     double best = -1.0;
-    int bi = 0;
+    int bi = 0, bh = 0;  // bh: upper word of the largest curvature among the samples preceding bi (0: none)
     walk(i0, i1 - i0, [&](int, int q, double k) {
         if constexpr (STAGED) KT[(size_t)q * G + g] = k;
-        if (k > best) { best = k; bi = q; }
+        const bool gt = k > best;
+        if (K1B_TIES) bh = gt ? __double2hiint(best) : bh;
+        best = gt ? k : best;
+        bi = gt ? q : bi;
     });
     K1B_STAMP(3);
-    // first maximum of the curvature == a minimum of v_local (velocity.py:34).  Lanes l, l+G, l+2G, ...
-    // hold consecutive chunks of one candidate: fold the upper lanes into the lower ones, lower chunk first
+    // Lanes l, l+G, l+2G, ... hold consecutive chunks of one candidate: fold the upper lanes into the lower ones,
+    // lower chunk first
 #pragma unroll
     for (int o = G; o < 32; o <<= 1) {
         const double ob = __shfl_down_sync(0xffffffffu, best, o);
+        const int oh = __shfl_down_sync(0xffffffffu, bh, o);
         const int oi = __shfl_down_sync(0xffffffffu, bi, o);
-        if ((lane % (2 * o)) < o && lane + o < 32 && ob > best) { best = ob; bi = oi; }
+        if ((lane % (2 * o)) < o && lane + o < 32 && ob > best) {
+            bh = max(__double2hiint(best), oh);  // curvatures are >= 0 or the -1 start value: signed order = value order
+            best = ob; bi = oi;
+        }
     }
-    if (lane < G) { RV[warp * G + lane] = best; RI[warp * G + lane] = bi; }
+    if (lane < G) { RV[warp * G + lane] = best; RH[warp * G + lane] = bh; RI[warp * G + lane] = bi; }
     __syncthreads();
+    bool tie = false;
     if (tid < G) {
         double bb = -1.0;
-        int bbi = 0;
+        int bbi = 0, bbh = 0;
         for (int w = 0; w < NW; ++w) {
             const double v = RV[w * G + tid];
-            if (v > bb) { bb = v; bbi = RI[w * G + tid]; }
+            if (v > bb) {
+                bbh = max(__double2hiint(bb), RH[w * G + tid]);
+                bb = v; bbi = RI[w * G + tid];
+            }
         }
         ROT[tid] = bbi;
-        a.rot[b0 + tid] = bbi;
+        KTHR[tid] = bb;  // the maximum (read again below if some candidate of the CTA has a tie to examine)
+        tie = K1B_TIES && bbh > 0 && bbh >= __double2hiint(bb) - 1;
+    }
+    if (__syncthreads_or(tie)) {  // rare: find the first sample of the plateau (all threads, CTA-uniform branch)
+        const double kmax = KTHR[g];
+        const double vmin = sqrt(a.mu_g / kmax), kthr = kmax * (1.0 - 0x1p-48);  // one ulp of k moves v_local by half an ulp
+        int first = 0x7fffffff;
+        auto look = [&](int q, double k) {
+            if (first == 0x7fffffff && k >= kthr && sqrt(a.mu_g / k) == vmin) first = q;
+        };
+        if constexpr (STAGED) {
+            for (int q = i0; q < i1; ++q) look(q, KT[(size_t)q * G + g]);
+        } else {
+            walk(i0, i1 - i0, [&](int, int q, double k) { look(q, k); });
+        }
+#pragma unroll
+        for (int o = G; o < 32; o <<= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+        if (lane < G) RI[warp * G + lane] = first;
+        __syncthreads();
+        if (tid < G) {
+            int f = 0x7fffffff;
+            for (int w = 0; w < NW; ++w) f = min(f, RI[w * G + tid]);
+            if (f < ROT[tid]) ROT[tid] = f;
+        }
+        __syncthreads();
+    }
+    if (tid < G) {
+        a.rot[b0 + tid] = ROT[tid];
         a.len[b0 + tid] = LEN[tid];
     }
-    __syncthreads();
     K1B_STAMP(4);
     // ---- W: write-out, rotated: row i of candidate g is sample (i + rot_g) mod n ----------------------------
     {

@@ -16,7 +16,7 @@ import torch
 import lap_time_optimization_b200 as ltk
 from conftest import case_setup, golden_cases, rel_err
 from oracle import c_oracle
-from oracle.reference_port import OracleTrack, load_vehicle, top_k
+from oracle.reference_port import OracleEvaluator, OracleTrack, load_vehicle, top_k
 
 pytestmark = pytest.mark.gpu
 PROFILE_KEYS = ("k", "v_local", "v_acclim", "v_declim", "v")
@@ -319,6 +319,37 @@ def make_oracle_only(name, spline):
     tj, width, vj, mode = case_setup(name)
     return None, c_oracle.COracle(OracleTrack(tj, width), load_vehicle(vj), mode, None, device_sum_order=True,
                                   spline=spline)
+
+
+@pytest.mark.parametrize("veh", ["tbr18", "MX5"])
+@pytest.mark.parametrize("spline", ["tridiagonal", "fitpack"])
+def test_plateau_curvature_circular_track(tmp_path, veh, spline):
+    """A circular corridor with regular cones: the curvature of symmetric candidates is a plateau whose samples
+    differ in the last bits only, so the arg-max of the curvature (the kernels' rotation) and the first arg-min of
+    v_local (velocity.py:34,58; both oracles) can name different samples.  Both are minima of v_local -- fixed points of
+    both sweeps -- so every lap time must still be the C oracle's bit for bit, and the port's to tolerance."""
+    import json
+
+    th = np.append(np.linspace(0.0, 2.0 * np.pi, 60, endpoint=False), 0.0)
+    doc = {"name": "circle", "left": {"x": list(50.0 * np.cos(th)), "y": list(50.0 * np.sin(th))},
+           "right": {"x": list(44.0 * np.cos(th)), "y": list(44.0 * np.sin(th))}}
+    tj = str(tmp_path / "circle.json")
+    with open(tj, "w") as fh:
+        json.dump(doc, fh)
+    vj = ltk.data_path("vehicles", veh + ".json")
+    for mode in ("bayes", "full"):
+        ev = ltk.LapTimeEvaluator(ltk.Track(tj, track_width=0.8, quiet=True), ltk.load_vehicle(vj), mode, None, spline=spline)
+        co = c_oracle.COracle(OracleTrack(tj, 0.8), load_vehicle(vj), mode, None, device_sum_order=True, spline=spline)
+        rng = np.random.default_rng(1)
+        a = np.vstack([np.full((1, ev.n_alpha), 0.5), np.full((1, ev.n_alpha), 0.25),          # perfect symmetry
+                       rng.uniform(0.45, 0.55, (30, ev.n_alpha)),                               # nearly circular
+                       np.tile(rng.uniform(0.0, 0.99, (32, 3)), (1, (ev.n_alpha + 2) // 3))[:, :ev.n_alpha]])  # period-3 patterns
+        got, want = ev.lap_times(a), co.lap_times(a)
+        assert np.array_equal(got, want), (mode, int((got != want).sum()))
+        port = OracleEvaluator(OracleTrack(tj, 0.8), load_vehicle(vj), mode)
+        ref = np.array([port.lap_time(x) for x in a[:3]])
+        assert np.max(np.abs(got[:3] - ref) / ref) < 1e-9
+        ev.close()
 
 
 # ---- properties ----------------------------------------------------------------------------------------
