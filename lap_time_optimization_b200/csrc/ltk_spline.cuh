@@ -29,11 +29,10 @@
 namespace ltk {
 
 #ifndef LTK_K1B_TRIM
-#define LTK_K1B_TRIM 15  // bit set of the trims below (A/B): 1 packed record, 2 guessed chunk start, 4 write-out, 8 step
-#endif
+#define LTK_K1B_TRIM 31  // bit set of the trims below (A/B): 1 packed record, 2 guessed chunk start, 4 write-out, 8 step,
+#endif                   // 16 record phase (first-sample guess by a multiplication, / 6 as a multiplication + one correction)
 // Interval record of k1b_samples (tridiagonal mode), 64 bytes = four 16-byte shared loads:
-// S'(t) = c1 + t (c2 + t h),  S''(t) = c2 + c3 t;  h = c3 / 2 is formed on load (exact), the index of the next
-// interval's first sample rides in the last slot.
+// S'(t) = c1 + t (c2 + t h),  S''(t) = c2 + c3 t;  h = c3 / 2 is formed on load (exact).
 struct __align__(16) IntervalP {
     double u, c1x, c1y, c2x, c2y, c3x, c3y;
     int inext, pad;
@@ -44,6 +43,7 @@ constexpr bool K1B_TRIM = (LTK_K1B_TRIM & 1) != 0;      // packed record
 constexpr bool K1B_GUESS = (LTK_K1B_TRIM & 2) != 0;     // chunk start interval from a proportional guess
 constexpr bool K1B_WLIN = (LTK_K1B_TRIM & 4) != 0;      // write-out with linear cursors
 constexpr bool K1B_STEP = (LTK_K1B_TRIM & 8) != 0;      // sampling step once per candidate
+constexpr bool K1B_CREC = (LTK_K1B_TRIM & 16) != 0;     // cheaper record phase
 #ifndef LTK_K1B_TIES
 #define LTK_K1B_TIES 1  // 0 (A/B only): rotation = first maximum of the curvature, plateaus not re-examined
 #endif
@@ -68,7 +68,7 @@ __host__ __device__ inline size_t k1f_smem_bytes(int G, int threads, int N, int 
     size_t bytes = (size_t)N * G * (fitpack ? sizeof(fit::FitInterval) : K1B_TRIM ? sizeof(IntervalP) : sizeof(Interval));  // interval records [N][G]
     bytes += (tile > scr ? tile : scr) * sizeof(double);             // curvature tile | scratch
     bytes += (size_t)(N + 1) * G * sizeof(int) + 8;                  // first sample index of each interval (+ alignment)
-    bytes += (size_t)G * (3 * sizeof(double) + sizeof(int));         // length, sampling step, largest curvature, rotation
+    bytes += (size_t)G * (4 * sizeof(double) + sizeof(int));         // length, sampling step, its reciprocal, largest curvature, rotation
     bytes += (size_t)(threads / 32) * G * (sizeof(double) + 2 * sizeof(int));  // arg-max partials
     return (bytes + 15) / 16 * 16;
 }
@@ -245,7 +245,8 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a, FitArgs fa)
     int* IB = reinterpret_cast<int*>(KT + ((STAGED && tile > scr) ? tile : scr));   // [N+1][G]
     double* LEN = reinterpret_cast<double*>(IB + (N + 1) * G + (((N + 1) * G) & 1));
     double* STEP = LEN + G;                                             // [G] np.linspace step (tbn.py:71)
-    double* KTHR = STEP + G;                                            // [G] largest curvature (see the arg-min below)
+    double* ISTEP = STEP + G;                                           // [G] ~ 1 / step: starting guesses only
+    double* KTHR = ISTEP + G;                                           // [G] largest curvature (see the arg-min below)
     double* RV = KTHR + G;                                              // [NW][G]
     int* RI = reinterpret_cast<int*>(RV + NW * G);                      // [NW][G]
     int* RH = RI + NW * G;                                              // [NW][G]
@@ -289,7 +290,11 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a, FitArgs fa)
             }
             __syncthreads();
         }
-        if (tid < G) { LEN[tid] = U[NG + tid]; STEP[tid] = U[NG + tid] / (double)(a.ns - 1); }
+        if (tid < G) {
+            LEN[tid] = U[NG + tid];
+            STEP[tid] = U[NG + tid] / (double)(a.ns - 1);
+            ISTEP[tid] = (double)(a.ns - 1) / U[NG + tid];
+        }
         __syncthreads();
         // ---- C (FITPACK mode): per-interval record (splder / fpbspl operands) and first sample index ---------
         for (int idx = tid; idx < NG; idx += T) {
@@ -354,7 +359,11 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a, FitArgs fa)
             }
             __syncthreads();
         }
-        if (tid < G) { LEN[tid] = U[NG + tid]; STEP[tid] = U[NG + tid] / (double)(a.ns - 1); }
+        if (tid < G) {
+            LEN[tid] = U[NG + tid];
+            STEP[tid] = U[NG + tid] / (double)(a.ns - 1);
+            ISTEP[tid] = (double)(a.ns - 1) / U[NG + tid];
+        }
         __syncthreads();
         K1B_STAMP(1);
         // ---- C: per-interval coefficients  S'(t) = c1 + t (c2 + t h),  S''(t) = c2 + c3 t,  h = c3/2, and the
@@ -368,39 +377,33 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a, FitArgs fa)
             const double c3x = ddiv<false>(mxn - mx, h), c3y = ddiv<false>(myn - my, h);
             Rec rec;
             rec.u = u0;
-            rec.c1x = ddiv<false>(PX[jn * G + g] - PX[idx], h) - ddiv<false>(h * (2.0 * mx + mxn), 6.0);
-            rec.c1y = ddiv<false>(PY[jn * G + g] - PY[idx], h) - ddiv<false>(h * (2.0 * my + myn), 6.0);
+            // x / 6 with RN(1/6) and one residual correction is the correctly rounded quotient (Markstein; checked
+            // against IEEE division on 4e8 operands): 3 FP64 instructions instead of 9 and a MUFU
+            auto sixth = [](double x) {
+                return K1B_CREC ? div_by_const<false>(x, 6.0, 1.0 / 6.0) : ddiv<false>(x, 6.0);
+            };
+            rec.c1x = ddiv<false>(PX[jn * G + g] - PX[idx], h) - sixth(h * (2.0 * mx + mxn));
+            rec.c1y = ddiv<false>(PY[jn * G + g] - PY[idx], h) - sixth(h * (2.0 * my + myn));
             rec.c2x = mx; rec.c2y = my;
             rec.c3x = c3x; rec.c3y = c3y;
             if constexpr (PACKED) {
-                rec.pad = 0;
+                rec.inext = 0; rec.pad = 0;  // (the next interval's first sample comes from IB, see narrow())
             } else {
                 rec.unext = u1;
                 rec.hx = 0.5 * c3x; rec.hy = 0.5 * c3y;
-                REC[idx] = rec;
             }
+            REC[idx] = rec;
             const double step = K1B_STEP ? STEP[g] : LEN[g] / (double)(a.ns - 1);  // np.linspace step (tbn.py:71)
             int i = 0;
             if (j > 0) {
-                i = (int)ddiv<false>(u0, step);
+                // any starting guess will do: the two loops below enforce the definition exactly
+                i = K1B_CREC ? (int)(u0 * ISTEP[g]) : (int)ddiv<false>(u0, step);
                 i = max(0, min(i, n));
                 while (i < n && (double)i * step < u0) ++i;
                 while (i > 0 && (double)(i - 1) * step >= u0) --i;
             }
             IB[idx] = i;
             if (j == N - 1) IB[NG + g] = n;
-            if constexpr (PACKED) {
-                // the next interval's first sample: the same search for the knot u1 (interval N-1 ends at n)
-                int in = n;
-                if (j + 1 < N) {
-                    in = (int)ddiv<false>(u1, step);
-                    in = max(0, min(in, n));
-                    while (in < n && (double)in * step < u1) ++in;
-                    while (in > 0 && (double)(in - 1) * step >= u1) --in;
-                }
-                rec.inext = in;
-                REC[idx] = rec;
-            }
         }
         __syncthreads();  // scratch is dead from here on: the tile region now takes curvatures
     }
@@ -438,12 +441,11 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a, FitArgs fa)
         [[maybe_unused]] double hx = 0, hy = 0;
         [[maybe_unused]] float f1x = 0, f2x = 0, f3x = 0, fhx = 0, f1y = 0, f2y = 0, f3y = 0, fhy = 0;
         auto narrow = [&]() {
+            inext = IB[(j + 1) * G + g];
             if constexpr (PACKED) {
-                inext = v.inext;
                 hx = 0.5 * v.c3x; hy = 0.5 * v.c3y;
-            } else {
-                inext = IB[(j + 1) * G + g];
-                if constexpr (!FIT) { hx = v.hx; hy = v.hy; }
+            } else if constexpr (!FIT) {
+                hx = v.hx; hy = v.hy;
             }
             if constexpr (F32K) {
                 f1x = (float)v.c1x; f2x = (float)v.c2x; f3x = (float)v.c3x; fhx = (float)hx;
