@@ -487,9 +487,11 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     cpu_result = None
     cpu_laps_base = None
+    cpu_one_core = None
     if world == 1 and not args.no_cpu_baseline:
         # the CPU baseline forks a worker pool: do it before this process owns a CUDA context
         cpu_result = cpu_rate(args, args.cpu_sample, os.cpu_count() or 1)
+        cpu_one_core = cpu_rate(args, 192, 1)[0]  # the rate at P cores and at one core
         try:
             cpu_laps_base = port_laps_baseline_dispatch(args, cpu_result[2])
         except Exception:  # the probe is extra evidence, not part of the contract
@@ -643,6 +645,10 @@ def run_ours(args):
                        None, 1 << 20, (2026, 4), True, peak, 3),
             run_config(D, ltk, local, "config 5: Buckmore resampled at 10,000 points per lap, 4,194,304 candidates", "tbr18",
                        10001, 1 << 22, (2026, 5), False, peak, 1),
+            # the middle point of SURVEY 8(d)'s sampling-density sweep Ns in {846, 2,500, 10,000} (the ends are the
+            # headline and config 5)
+            run_config(D, ltk, local, "sampling-density sweep: 2,500 points per lap, 1,048,576 candidates", "tbr18",
+                       2501, 1 << 20, (2026, 6), False, peak, 1),
         ]
     probe = h2d_probe(D, B * na * 8)
 
@@ -689,6 +695,10 @@ def run_ours(args):
                          # 2 cycles per FP64 warp instruction and scheduler, 3 for a three-register DFMA)
                          "fp64_pipe": fp64_pipe_model(args, B, n, ms_total / args.steps, clocks),
                          "issue_model": issue_model(args, B, n, ms_total / args.steps, clocks),
+                         # SURVEY 8(d) figure 2, the compulsory-traffic floor of a fully fused pipeline (alphas in,
+                         # lap time out): how far from memory-bound the arithmetic is
+                         "compulsory": {"bytes_per_candidate": 8 * na + 8,
+                                        "frac": (8 * na + 8) * B / (ms_total / args.steps * 1e-3) / 1e9 / peak},
                          "pipeline": {"bytes_per_candidate": a_staged,
                                       "achieved": a_staged * B * world / (ms_total / args.steps * 1e-3) / 1e9 / world,
                                       "frac": a_staged * B / (ms_total / args.steps * 1e-3) / 1e9 / peak}},
@@ -698,7 +708,7 @@ def run_ours(args):
         if cpu_result is not None:
             cores = os.cpu_count() or 1
             rate, cpu_laps, cpu_a = cpu_result
-            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "one_core": cpu_one_core,
                                     "sample": f"{args.cpu_sample} candidates of the timed population, warm fork pool of {cores} "
                                               "processes, oracle/reference_port.py",
                                     "parity_rel_err": parity[args.spline]}
