@@ -344,10 +344,9 @@ def topk_identity(D, ev, pop, base, finish):
     """One population per rank through the production path (pipeline -> local top-k -> all-gather -> merge);
     then EVERY lap time goes to rank 0, which sorts them on the host (stable: what `sorted(...)[0:10]` does at
     trajectory_bayesian_nonlinear.py:253-257) and compares indices and values with the merged device result."""
-    d_lap = ev.lap_times_device(pop)
-    best, idx = ev.topk_device(d_lap, TOPK, index_base=base)
+    d_lap, best, idx, packed = ev.lap_times_topk_device(pop, k=TOPK, index_base=base, packed=True)
     if finish is not None:
-        best, idx = finish(best, idx)
+        best, idx = finish(packed) if getattr(finish, "packed", False) else finish(best, idx)
     all_laps = D.gather_rows(d_lap).cpu().numpy()  # rank r's rows sit at [r * B, (r + 1) * B) = its global indices
     h_idx, h_best = stable_topk(all_laps, TOPK)
     same = bool(np.array_equal(h_idx, idx.cpu().numpy()) and np.array_equal(h_best, best.cpu().numpy()))
@@ -384,7 +383,7 @@ def run_config(D, ltk, local, tag, vehicle, ns, total, key, timed_generation, pe
     [r * total / N, (r + 1) * total / N) of ONE Philox population on its GPU, scores them, takes its local
     top-10 with global indices; all-gather + merge.  Checks: merged top-10 == stable host sort of all lap
     times; a subsample of rank 0's shard == the C oracle bit for bit; the device population == numpy's Philox."""
-    from lap_time_optimization_b200.distributed import allgather_topk, shard_bounds
+    from lap_time_optimization_b200.distributed import PackedTopkGather, shard_bounds
 
     torch = D.torch
     tj, vj = data_paths(vehicle)
@@ -396,10 +395,9 @@ def run_config(D, ltk, local, tag, vehicle, ns, total, key, timed_generation, pe
 
     def once(generate):
         a = ev.random_population_device(Bl, key, first_row=lo) if generate else d_a
-        d_lap = ev.lap_times_device(a, out=out)
-        best, idx = ev.topk_device(d_lap, TOPK, index_base=lo)
+        d_lap, best, idx, packed = ev.lap_times_topk_device(a, out=out, k=TOPK, index_base=lo, packed=True)
         if D.world > 1:
-            best, idx = allgather_topk(best, idx, TOPK, merge=ev.merge_topk_device)
+            best, idx = PackedTopkGather(ev, TOPK)(packed)
         return a, d_lap, best, idx
 
     # warm-up on a slice: lanes, workspaces and the top-k scratch exist before the clock starts
@@ -480,7 +478,7 @@ def run_ours(args):
     import torch.distributed as dist
     import lap_time_optimization_b200 as ltk
     from lap_time_optimization_b200 import _native
-    from lap_time_optimization_b200.distributed import allgather_topk
+    from lap_time_optimization_b200.distributed import PackedTopkGather, allgather_topk
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -524,7 +522,12 @@ def run_ours(args):
     LANES = args.lanes  # populations in flight (LapTimeEvaluator.lanes): kernels of different steps overlap
     d_laps = [torch.empty(B, dtype=torch.float64, device=dev) for _ in range(LANES)]
     d_lap = d_laps[0]
-    finish = (lambda b, ix: allgather_topk(b, ix, TOPK, merge=ev.merge_topk_device)) if world > 1 else None
+    # the cross-rank step of every population: one all-gather of the packed top-10 list + one merge launch
+    # (LTK_BENCH_FINISH=unpacked: the five-launch route through allgather_topk, for A/B)
+    if world > 1 and os.environ.get("LTK_BENCH_FINISH") == "unpacked":
+        finish = lambda b, ix: allgather_topk(b, ix, TOPK, merge=ev.merge_topk_device)
+    else:
+        finish = PackedTopkGather(ev, TOPK) if world > 1 else None
 
     def run_steps(nsteps):
         return ev.run_resident((dev_sets[i % N_INPUT_SETS] for i in range(nsteps)), d_laps, TOPK, index_base=base,
@@ -564,6 +567,14 @@ def run_ours(args):
     #      byte of every step still crosses PCIe inside the timed region. ------------------------------
     pin_in = [torch.as_tensor(h).pin_memory() for h in host_sets[:4]]
     e2e_finish = None if os.environ.get("LTK_BENCH_E2E_NO_FINISH") else finish  # diagnostic: e2e without the all-gather
+    if world > 1 and os.environ.get("LTK_BENCH_E2E_FINISH") == "merge_only":    # diagnostics: which half of it costs
+        e2e_finish = lambda b, ix: ev.merge_topk_device(torch.cat([b] * world), torch.cat([ix] * world), TOPK)
+    if world > 1 and os.environ.get("LTK_BENCH_E2E_FINISH") == "nccl_only":
+        def e2e_finish(b, ix):
+            packed = torch.cat([b.view(torch.int64), ix])
+            gathered = torch.empty(world * packed.numel(), dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(gathered, packed)
+            return b, ix
     def e2e_run(nsteps):
         checksum = 0.0
         for laps, best_h, idx_h in ev.stream_populations((pin_in[i % 4] for i in range(nsteps)), TOPK,

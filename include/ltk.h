@@ -222,6 +222,15 @@ int ltk_topk_pairs(ltk_ctx *ctx, const double *d_lap, const int64_t *d_idx, int6
 
 /* Library/ABI version and a count of kernel launches issued through this library since load
  * (bench.py reports it as gpu_launches). */
+/* The cross-rank half of the multi-GPU selection in one launch: d_gathered is the all-gathered buffer
+ * [world][2][k_in] of int64 -- per rank, k_in lap times as bit patterns followed by k_in global indices, i.e. what
+ * ltk_eval_alphas_topk leaves on a rank when it is given d_best_lap = buf and d_best_idx = buf + k_in -- and the
+ * result is the stable top-k of all world * k_in pairs (entries with index < 0 are padding).  One collective
+ * (all-gather of 16 k_in bytes per rank) and this call replace `sorted(results)[0:10]` over the ranks' lists
+ * (trajectory_bayesian_nonlinear.py:253-257).  world * k_in <= 1,024. */
+int ltk_topk_gathered(ltk_ctx *ctx, const int64_t *d_gathered, int world, int k_in, int k, double *d_best_lap,
+                      int64_t *d_best_idx, void *stream);
+
 int ltk_version(void);
 int64_t ltk_launch_count(void);
 

@@ -54,6 +54,7 @@ SIGNATURES = {
     "ltk_eval_objectives": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _vp, C.c_size_t, _vp]),
     "ltk_random_uniform": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_int64, C.c_int64, C.c_double, C.c_double, _vp, _vp]),
     "ltk_topk_pairs": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int, _vp, _vp, _vp]),
+    "ltk_topk_gathered": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
     "ltk_eval_controls": (C.c_int, [_vp, _vp, C.c_int, C.c_int64, _vp, _vp, C.c_size_t, _vp]),
     "ltk_profile": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ltk_topk": (C.c_int, [_vp, _vp, C.c_int64, C.c_int64, C.c_int, _vp, _vp, _vp]),

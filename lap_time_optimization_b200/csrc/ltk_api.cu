@@ -1084,6 +1084,21 @@ int ltk_topk_pairs(ltk_ctx* ctx, const double* d_lap, const int64_t* d_idx, int6
                     reinterpret_cast<long long*>(d_best_idx), static_cast<cudaStream_t>(stream));
 }
 
+int ltk_topk_gathered(ltk_ctx* ctx, const int64_t* d_gathered, int world, int k_in, int k, double* d_best_lap,
+                      int64_t* d_best_idx, void* stream)
+{
+    if (!ctx) return LTK_E_ARG;
+    if (!d_gathered || !d_best_lap || !d_best_idx || world < 1 || k_in < 1) return fail(ctx, LTK_E_ARG, "null or non-positive argument");
+    if (k < 1 || k > TOPK_MAX) return fail(ctx, LTK_E_ARG, "k must be in 1..64");
+    if ((long long)world * k_in > TOPK_BLOCK_KEYS) return fail(ctx, LTK_E_UNSUPPORTED, "world * k_in exceeds one merge block (1,024 keys)");
+    DeviceGuard guard(ctx->device);
+    topk_merge_gathered<<<1, TOPK_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const long long*>(d_gathered), world, k_in, k, d_best_lap, reinterpret_cast<long long*>(d_best_idx));
+    g_launches.fetch_add(1);
+    LTK_CUDA(ctx, cudaGetLastError());
+    return LTK_OK;
+}
+
 int ltk_eval_controls(ltk_ctx* ctx, const double* d_xy, int m, int64_t B, double* d_lap, void* d_workspace,
                       size_t workspace_bytes, void* stream)
 {

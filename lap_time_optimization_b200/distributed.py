@@ -47,9 +47,30 @@ def allgather_topk(local_laps, local_idx, k, group=None, merge=merge_topk):
     return merge(laps, idx, k)
 
 
+class PackedTopkGather:
+    """The cross-rank step as `finish` hook of `LapTimeEvaluator.stream_populations` / `run_resident`: ONE all-gather of the
+    rank's packed top-k list (int64 [2k]: lap bit patterns, global indices -- written in place by the sweep kernel's
+    epilogue) and ONE merge launch on the gathered buffer (`ltk_topk_gathered`).  The unpacked route (`allgather_topk`)
+    needs a concatenation before and two re-packing copies after the collective: five small launches per population on
+    the communication stream instead of two."""
+
+    packed = True
+
+    def __init__(self, evaluator, k, group=None):
+        self.ev, self.k, self.group = evaluator, int(k), group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+
+    def __call__(self, packed):
+        if self.world == 1:
+            return packed[:self.k].view(torch.float64), packed[self.k:]
+        gathered = torch.empty(self.world * packed.numel(), dtype=torch.int64, device=packed.device)
+        dist.all_gather_into_tensor(gathered, packed, group=self.group)
+        return self.ev.merge_gathered_device(gathered, self.world, packed.numel() // 2, self.k)
+
+
 def sharded_population_topk(evaluator, local_alphas, index_base, k, group=None):
     """Score this rank's shard on its GPU, local top-k with global indices, all-gather, merge.
     Returns (local_laps [B_local] CUDA, best_laps[k], best_idx[k])."""
-    d_lap, best, idx = evaluator.lap_times_topk_device(local_alphas, k=k, index_base=index_base)
-    g_best, g_idx = allgather_topk(best, idx, k, group, merge=evaluator.merge_topk_device)
+    d_lap, _best, _idx, packed = evaluator.lap_times_topk_device(local_alphas, k=k, index_base=index_base, packed=True)
+    g_best, g_idx = PackedTopkGather(evaluator, k, group)(packed)
     return d_lap, g_best, g_idx

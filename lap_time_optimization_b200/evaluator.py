@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import sys
 import math
 
 import numpy as np
@@ -309,6 +310,17 @@ class LapTimeEvaluator:
         _native.check(rc, self._ctx)
         return best, out_idx
 
+    def merge_gathered_device(self, gathered, world, k_in, k=DEFAULT_TOPK):
+        """Stable top-k of an all-gathered buffer [world][2][k_in] (int64: lap bit patterns, then global indices per
+        rank -- `lap_times_topk_device(..., packed=True)`'s fourth result on every rank) in one launch."""
+        torch = self.torch
+        best = torch.empty(k, dtype=torch.float64, device=self.device)
+        out_idx = torch.empty(k, dtype=torch.int64, device=self.device)
+        rc = self.lib.ltk_topk_gathered(self._ctx, _device.ptr(gathered), int(world), int(k_in), int(k),
+                                        _device.ptr(best), _device.ptr(out_idx), _device.stream_ptr(torch, self.device))
+        _native.check(rc, self._ctx)
+        return best, out_idx
+
     def controls_lap_times_device(self, xy, out=None):
         """xy: float64 CUDA tensor [B, 2, n_alpha + 1] of control points (calcMinTime surface)."""
         torch = self.torch
@@ -409,6 +421,7 @@ class LapTimeEvaluator:
                     "h_best": torch.empty(k, dtype=torch.float64).pin_memory(),
                     "h_idx": torch.empty(k, dtype=torch.int64).pin_memory(),
                     "ev_in": torch.cuda.Event(), "ev_done": torch.cuda.Event(), "ev_out": torch.cuda.Event(),
+                    "ev_fin": torch.cuda.Event(),
                     "used": False}
 
         def take(entry):
@@ -418,11 +431,18 @@ class LapTimeEvaluator:
             return sl["h_lap"][:B].numpy(), sl["h_best"].numpy(), sl["h_idx"].numpy()
 
         base = int(index_base)
+        prof = {"take": 0.0, "finish": 0.0, "total": 0.0, "n": 0} if os.environ.get("LTK_E2E_PROFILE") else None
+        import time as _time
+        t_loop = _time.perf_counter()
         for i, pop in enumerate(populations):
             si = i % nslot
             lane = pool[i % len(pool)]
             if len(pending) == nslot:  # the slot about to be reused still holds an untaken result
-                yield take(pending.pop(0))
+                t0_ = _time.perf_counter()
+                res_ = take(pending.pop(0))
+                if prof is not None:
+                    prof["take"] += _time.perf_counter() - t0_
+                yield res_
             t = pop if hasattr(pop, "is_pinned") else torch.from_numpy(np.ascontiguousarray(pop, dtype=np.float64))
             if t.dim() != 2 or t.shape[1] != self.n_alpha or t.dtype != torch.float64:
                 raise ValueError(f"populations must be float64 [B, {self.n_alpha}]")
@@ -447,14 +467,23 @@ class LapTimeEvaluator:
                 lane.stream.wait_event(sl["ev_in"])
                 if sl["used"]:
                     lane.stream.wait_event(sl["ev_out"])  # d_lap of this slot has been read back
-                d_lap, best, idx = lane.ev.lap_times_topk_device(sl["d_in"][:B], out=sl["d_lap"][:B], k=k,
-                                                                 index_base=base, _lane=len(pool) > 1)
+                d_lap, best, idx, pk = lane.ev.lap_times_topk_device(sl["d_in"][:B], out=sl["d_lap"][:B], k=k,
+                                                                     index_base=base, _lane=len(pool) > 1, packed=True)
                 sl["ev_done"].record(lane.stream)
             if finish is not None:
-                best, idx = self._finish_async(finish, best, idx, sl["ev_done"])
+                # the cross-rank step gets an event of its own: the slot's upload buffer is free again once this
+                # rank's kernels are done (ev_done), and the lap times go home then -- only the k best wait for the
+                # other ranks (with one event for both, every rank's uploads stalled behind the slowest rank's)
+                fin = sl["ev_done"] if os.environ.get("LTK_E2E_COUPLED") else sl["ev_fin"]  # (A/B: the old single event)
+                t0_ = _time.perf_counter()
+                best, idx = self._finish_async(finish, best, idx, sl["ev_done"], fin, pk)
+                if prof is not None:
+                    prof["finish"] += _time.perf_counter() - t0_
             with torch.cuda.stream(copy_out):
                 copy_out.wait_event(sl["ev_done"])
                 sl["h_lap"][:B].copy_(d_lap, non_blocking=True)
+                if finish is not None:
+                    copy_out.wait_event(fin)
                 sl["h_best"].copy_(best, non_blocking=True)
                 sl["h_idx"].copy_(idx, non_blocking=True)
                 sl["ev_out"].record(copy_out)
@@ -462,6 +491,11 @@ class LapTimeEvaluator:
             sl["used"] = True
             pending.append((si, B))
             base += B if index_stride is None else int(index_stride)
+        if prof is not None:
+            prof["total"] = _time.perf_counter() - t_loop
+            n_ = max(1, i + 1)
+            print(f"[stream_populations] host per population: loop {1e6 * prof['total'] / n_:.0f} us, of which blocked in take "
+                  f"{1e6 * prof['take'] / n_:.0f} us, in finish {1e6 * prof['finish'] / n_:.0f} us", file=sys.stderr, flush=True)
         while pending:
             yield take(pending.pop(0))
 
@@ -481,23 +515,25 @@ class LapTimeEvaluator:
         for i, pop in enumerate(populations):
             lane = pool[i % len(pool)]
             with torch.cuda.stream(lane.stream):
-                last = lane.ev.lap_times_topk_device(pop, out=outs[i % len(pool)], k=k, index_base=index_base,
-                                                     _lane=len(pool) > 1)[1:]
+                res = lane.ev.lap_times_topk_device(pop, out=outs[i % len(pool)], k=k, index_base=index_base,
+                                                    _lane=len(pool) > 1, packed=True)
+                last, pk = res[1:3], res[3]
                 if finish is not None:
                     done = torch.cuda.Event()
                     done.record(lane.stream)
             if finish is not None:
-                last = self._finish_async(finish, last[0], last[1], done)
+                last = self._finish_async(finish, last[0], last[1], done, None, pk)
         for st in [lane.stream for lane in pool] + ([self._comm_stream] if finish is not None else []):
             done = torch.cuda.Event()
             done.record(st)
             main.wait_event(done)
         return last
 
-    def _finish_async(self, finish, best, idx, ready):
+    def _finish_async(self, finish, best, idx, ready, done=None, packed=None):
         """Run the cross-rank step (all-gather + merge) of one population on a communication stream of its
         own: the lane that produced (best, idx) goes straight on to its next population instead of
-        waiting out the collective's latency.  `ready` is re-recorded when the result is complete."""
+        waiting out the collective's latency.  `done` (default: `ready` itself) is recorded when the result is
+        complete."""
         torch = self.torch
         if getattr(self, "_comm_stream", None) is None:
             self._comm_stream = torch.cuda.Stream(self.device)
@@ -506,34 +542,44 @@ class LapTimeEvaluator:
             comm.wait_event(ready)
             best.record_stream(comm)
             idx.record_stream(comm)
-            out = finish(best, idx)
-            ready.record(comm)
+            if packed is not None and getattr(finish, "packed", False):
+                packed.record_stream(comm)
+                out = finish(packed)  # one collective on the packed list, one merge launch (distributed.PackedTopkGather)
+            else:
+                out = finish(best, idx)
+            (done if done is not None else ready).record(comm)
         return out
 
-    def lap_times_topk_device(self, alphas, out=None, k=DEFAULT_TOPK, index_base=0, _lane=False):
+    def lap_times_topk_device(self, alphas, out=None, k=DEFAULT_TOPK, index_base=0, _lane=False, packed=False):
         """`lap_times_device` and `topk_device` of the same population in one call: -> (laps[B], best[k], idx[k])
         CUDA tensors.  A population that fits one chunk goes through `ltk_eval_alphas_topk` -- the k best are
         selected in the sweep kernel's epilogue, no separate selection launch; anything else (multi-wave
-        populations, chunked workspaces) scores first and selects afterwards.  Asynchronous on the current stream."""
+        populations, chunked workspaces) scores first and selects afterwards.  Asynchronous on the current stream.
+        `packed=True` adds a fourth result: the int64 tensor [2k] that `best` (as bit patterns) and `idx` are the two
+        halves of -- the unit of the multi-GPU all-gather (`distributed.PackedTopkGather`)."""
         torch = self.torch
         B = alphas.shape[0]
         if (alphas.dtype != torch.float64 or not alphas.is_cuda or alphas.dim() != 2 or alphas.shape[1] != self.n_alpha
                 or not alphas.is_contiguous() or B < 1 or (B >= 2 * self.WAVE and self.wave_lanes > 1)
                 or B > self.max_batch()):
             laps = self.lap_times_device(alphas, out=out, _lane=_lane)
-            return (laps,) + tuple(self.topk_device(laps, k, index_base=index_base))
+            best, idx = self.topk_device(laps, k, index_base=index_base)
+            if packed:
+                pk = torch.cat([best.view(torch.int64), idx])
+                return laps, pk[:k].view(torch.float64), pk[k:], pk
+            return laps, best, idx
         if out is None:
             out = torch.empty(B, dtype=torch.float64, device=self.device)
         if not _lane:
             self._set_split(True)
-        best = torch.empty(k, dtype=torch.float64, device=self.device)
-        idx = torch.empty(k, dtype=torch.int64, device=self.device)
+        pk = torch.empty(2 * k, dtype=torch.int64, device=self.device)
+        best, idx = pk[:k].view(torch.float64), pk[k:]
         ws = self._workspace(B)
         rc = self.lib.ltk_eval_alphas_topk(self._ctx, _device.ptr(alphas), B, _device.ptr(out), _device.ptr(ws),
                                            ws.numel(), int(index_base), int(k), _device.ptr(best), _device.ptr(idx),
                                            _device.stream_ptr(torch, self.device))
         _native.check(rc, self._ctx)
-        return out, best, idx
+        return (out, best, idx, pk) if packed else (out, best, idx)
 
     def topk_device(self, laps, k=DEFAULT_TOPK, index_base=0):
         """Stable ascending top-k of a CUDA lap tensor -> (lap[k], idx[k]) CUDA tensors."""

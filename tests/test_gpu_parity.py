@@ -532,6 +532,31 @@ def test_sharded_population_topk_single_rank(buckmore):
     assert np.array_equal(i.cpu().numpy(), o_idx) and np.array_equal(b.cpu().numpy(), o_best)
 
 
+def test_gathered_merge_of_packed_topk_lists(buckmore):
+    """The cross-rank step as the multi-GPU path runs it: every rank's sweep epilogue leaves a packed list (lap bit
+    patterns, global indices), the lists are all-gathered as they are and merged in one launch (ltk_topk_gathered).
+    Emulated on one GPU with three shards, a duplicated candidate across shards (tie -> lower global index) and a short
+    last shard; against a stable host sort."""
+    from lap_time_optimization_b200.distributed import shard_bounds
+
+    ev, co = buckmore
+    a = np.random.default_rng(23).uniform(0.0, 0.99, (3001, ev.n_alpha))
+    a[2500] = a[7]
+    ref = co.lap_times(a)
+    lists = []
+    for r in range(3):
+        lo, hi = shard_bounds(len(a), r, 3)
+        _, best, idx, packed = ev.lap_times_topk_device(torch.as_tensor(a[lo:hi]).cuda(), k=10, index_base=lo, packed=True)
+        assert packed.dtype == torch.int64 and packed.numel() == 20
+        assert torch.equal(packed[:10].view(torch.float64), best) and torch.equal(packed[10:], idx)
+        lists.append(packed)
+    b, i = ev.merge_gathered_device(torch.cat(lists), 3, 10, 10)
+    o_idx, o_best = top_k(list(ref), 10)
+    assert np.array_equal(i.cpu().numpy(), o_idx) and np.array_equal(b.cpu().numpy(), o_best)
+    b4, i4 = ev.merge_gathered_device(torch.cat(lists), 3, 10, 4)
+    assert np.array_equal(i4.cpu().numpy(), o_idx[:4])
+
+
 # ---- the reference's call surface -------------------------------------------------------------------------
 def test_trajectory_facades(golden):
     g = golden("buckmore_tbr18_full")
