@@ -403,6 +403,7 @@ def run_config(D, ltk, local, tag, vehicle, ns, total, key, timed_generation, pe
     # warm-up on a slice: lanes, workspaces and the top-k scratch exist before the clock starts
     ev.lap_times_device(d_a[:min(Bl, 3 * ev.WAVE)], out=out[:min(Bl, 3 * ev.WAVE)])
     ev.topk_device(out, TOPK, index_base=lo)
+    once(False)  # one full pass (cross-rank gather and merge included) before the clock starts
     if timed_generation:  # two generated populations are alive at a time: let the caching allocator own both blocks
         keep = once(True)
         once(True)
