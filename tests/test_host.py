@@ -160,6 +160,56 @@ def test_allgather_topk_gloo_world2():
     assert expect[:2] == [17, 900]
 
 
+class _HostMerge:
+    """Stand-in for LapTimeEvaluator.merge_gathered_device on a machine without a GPU: the same selection from the
+    gathered [world][2][k_in] layout, in torch."""
+
+    @staticmethod
+    def merge_gathered_device(gathered, world, k_in, k):
+        g = gathered.view(world, 2, k_in)
+        return merge_topk(g[:, 0, :].contiguous().view(torch.float64).reshape(-1), g[:, 1, :].reshape(-1), k)
+
+
+def _gloo_packed_worker(rank, world, port, k, q):
+    import torch.distributed as dist
+
+    from lap_time_optimization_b200.distributed import PackedTopkGather
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    rng = np.random.default_rng(12)
+    laps_all = rng.uniform(40, 50, 1001)  # uneven shards
+    laps_all[3] = laps_all[777] = 38.5
+    lo, hi = shard_bounds(1001, rank, world)
+    local = torch.tensor(laps_all[lo:hi])
+    order = torch.sort(local, stable=True).indices[:k]
+    packed = torch.cat([local[order].view(torch.int64), order + lo])  # what the sweep epilogue leaves on a rank
+    best, idx = PackedTopkGather(_HostMerge(), k)(packed)
+    q.put((rank, best.tolist(), idx.tolist()))
+    dist.destroy_process_group()
+
+
+def test_packed_topk_gather_gloo_world2():
+    """The multi-GPU cross-rank step (one all-gather of the packed list, one merge of the gathered layout) with two
+    gloo ranks on the CPU; the merge kernel itself is checked on the GPU (test_gathered_merge_of_packed_topk_lists)."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_packed_worker, args=(r, 2, port, 10, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+    rng = np.random.default_rng(12)
+    laps_all = rng.uniform(40, 50, 1001)
+    laps_all[3] = laps_all[777] = 38.5
+    expect = sorted(range(1001), key=lambda i: laps_all[i])[:10]
+    assert out[0][2] == expect and out[1][2] == expect and out[0][1] == out[1][1]
+    assert expect[:2] == [3, 777]
+
+
 def test_result_artefact_writers(tmp_path):
     """The JSON files of src/__main__.py:196-213 / utils.py:108-136 (what mpc/track.py reads back)."""
     import json
