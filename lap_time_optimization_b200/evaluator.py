@@ -8,6 +8,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import sys
+import time
 import math
 
 import numpy as np
@@ -431,17 +432,17 @@ class LapTimeEvaluator:
             return sl["h_lap"][:B].numpy(), sl["h_best"].numpy(), sl["h_idx"].numpy()
 
         base = int(index_base)
-        prof = {"take": 0.0, "finish": 0.0, "total": 0.0, "n": 0} if os.environ.get("LTK_E2E_PROFILE") else None
-        import time as _time
-        t_loop = _time.perf_counter()
+        # LTK_E2E_PROFILE=1: where the host thread's time goes (blocked on results / in the cross-rank hook / the rest)
+        prof = {"take": 0.0, "finish": 0.0, "n": 0} if os.environ.get("LTK_E2E_PROFILE") else None
+        t_loop = time.perf_counter()
         for i, pop in enumerate(populations):
             si = i % nslot
             lane = pool[i % len(pool)]
             if len(pending) == nslot:  # the slot about to be reused still holds an untaken result
-                t0_ = _time.perf_counter()
+                t0_ = time.perf_counter()
                 res_ = take(pending.pop(0))
                 if prof is not None:
-                    prof["take"] += _time.perf_counter() - t0_
+                    prof["take"] += time.perf_counter() - t0_
                 yield res_
             t = pop if hasattr(pop, "is_pinned") else torch.from_numpy(np.ascontiguousarray(pop, dtype=np.float64))
             if t.dim() != 2 or t.shape[1] != self.n_alpha or t.dtype != torch.float64:
@@ -475,10 +476,11 @@ class LapTimeEvaluator:
                 # rank's kernels are done (ev_done), and the lap times go home then -- only the k best wait for the
                 # other ranks (with one event for both, every rank's uploads stalled behind the slowest rank's)
                 fin = sl["ev_done"] if os.environ.get("LTK_E2E_COUPLED") else sl["ev_fin"]  # (A/B: the old single event)
-                t0_ = _time.perf_counter()
+                t0_ = time.perf_counter()
                 best, idx = self._finish_async(finish, best, idx, sl["ev_done"], fin, pk)
                 if prof is not None:
-                    prof["finish"] += _time.perf_counter() - t0_
+                    prof["finish"] += time.perf_counter() - t0_
+                    prof["n"] = i + 1
             with torch.cuda.stream(copy_out):
                 copy_out.wait_event(sl["ev_done"])
                 sl["h_lap"][:B].copy_(d_lap, non_blocking=True)
@@ -492,9 +494,8 @@ class LapTimeEvaluator:
             pending.append((si, B))
             base += B if index_stride is None else int(index_stride)
         if prof is not None:
-            prof["total"] = _time.perf_counter() - t_loop
-            n_ = max(1, i + 1)
-            print(f"[stream_populations] host per population: loop {1e6 * prof['total'] / n_:.0f} us, of which blocked in take "
+            n_ = max(1, prof["n"], len(pending))
+            print(f"[stream_populations] host per population: loop {1e6 * (time.perf_counter() - t_loop) / n_:.0f} us, of which blocked in take "
                   f"{1e6 * prof['take'] / n_:.0f} us, in finish {1e6 * prof['finish'] / n_:.0f} us", file=sys.stderr, flush=True)
         while pending:
             yield take(pending.pop(0))
