@@ -438,6 +438,8 @@ class LapTimeEvaluator:
         for i, pop in enumerate(populations):
             si = i % nslot
             lane = pool[i % len(pool)]
+            if prof is not None:
+                prof["n"] = i + 1
             if len(pending) == nslot:  # the slot about to be reused still holds an untaken result
                 t0_ = time.perf_counter()
                 res_ = take(pending.pop(0))
@@ -480,7 +482,6 @@ class LapTimeEvaluator:
                 best, idx = self._finish_async(finish, best, idx, sl["ev_done"], fin, pk)
                 if prof is not None:
                     prof["finish"] += time.perf_counter() - t0_
-                    prof["n"] = i + 1
             with torch.cuda.stream(copy_out):
                 copy_out.wait_event(sl["ev_done"])
                 sl["h_lap"][:B].copy_(d_lap, non_blocking=True)
@@ -494,7 +495,7 @@ class LapTimeEvaluator:
             pending.append((si, B))
             base += B if index_stride is None else int(index_stride)
         if prof is not None:
-            n_ = max(1, prof["n"], len(pending))
+            n_ = max(1, prof["n"])
             print(f"[stream_populations] host per population: loop {1e6 * (time.perf_counter() - t_loop) / n_:.0f} us, of which blocked in take "
                   f"{1e6 * prof['take'] / n_:.0f} us, in finish {1e6 * prof['finish'] / n_:.0f} us", file=sys.stderr, flush=True)
         while pending:
