@@ -44,6 +44,9 @@ constexpr bool K1B_GUESS = (LTK_K1B_TRIM & 2) != 0;     // chunk start interval 
 constexpr bool K1B_WLIN = (LTK_K1B_TRIM & 4) != 0;      // write-out with linear cursors
 constexpr bool K1B_STEP = (LTK_K1B_TRIM & 8) != 0;      // sampling step once per candidate
 constexpr bool K1B_CREC = (LTK_K1B_TRIM & 16) != 0;     // cheaper record phase
+#ifndef LTK_K1B_PREFETCH
+#define LTK_K1B_PREFETCH 0  // > 0: every CTA bulk-prefetches into L2 the inputs of the CTA that many blocks ahead
+#endif
 #ifndef LTK_K1B_TIES
 #define LTK_K1B_TIES 1  // 0 (A/B only): rotation = first maximum of the curvature, plateaus not re-examined
 #endif
@@ -338,6 +341,18 @@ __global__ void __launch_bounds__(T, MINB) k1b_samples(K1Args a, FitArgs fa)
                 mbar_expect_tx(&mbar, bytes);
                 bulk_g2s(U, a.hand + (size_t)blockIdx.x * rows * HAND_G, bytes, &mbar);
             }
+#if LTK_K1B_PREFETCH
+            // the CTA that will run on this slot a couple of generations from now starts with two cold reads (its
+            // packed hand-off block and its four alpha rows): pull them into L2 now
+            if (tid == 32 && a.mode == 0) {
+                const long long nb = (long long)blockIdx.x + LTK_K1B_PREFETCH;
+                if ((nb + 1) * G <= a.B) {
+                    bulk_prefetch_l2(a.hand + (size_t)nb * rows * HAND_G, (unsigned)rows * HAND_G * sizeof(double));
+                    const double* al = a.alphas + (size_t)nb * G * N;  // 4 rows of N doubles, 32 N bytes: 16-byte multiple
+                    bulk_prefetch_l2(al, (unsigned)(G * N * sizeof(double)));
+                }
+            }
+#endif
         }
         {   // T / G threads per candidate, j fastest: a candidate's alpha row is contiguous (no division by N)
             const int g = tid / CPT;
