@@ -19,7 +19,21 @@ def pytest_configure(config):
 def golden_cases():
     names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
     # objectives_*: tools/make_golden_objectives.py, compromise_*: tools/make_golden_compromise.py
-    return [n for n in names if not n.startswith(("objectives_", "compromise_"))]
+    # plateau_*: tools/make_golden_plateau.py (a synthetic circular corridor, generated on the fly by its tests)
+    return [n for n in names if not n.startswith(("objectives_", "compromise_", "plateau_"))]
+
+
+def circle_track_json(directory, g):
+    """The circular corridor of tests/golden/plateau_circle.npz (tools/make_golden_plateau.py::circle_doc)."""
+    import json
+
+    th = np.append(np.linspace(0.0, 2.0 * np.pi, int(g["n_cones"]), endpoint=False), 0.0)
+    doc = {"name": "circle", "left": {"x": list(float(g["r_out"]) * np.cos(th)), "y": list(float(g["r_out"]) * np.sin(th))},
+           "right": {"x": list(float(g["r_in"]) * np.cos(th)), "y": list(float(g["r_in"]) * np.sin(th))}}
+    path = os.path.join(str(directory), "circle.json")
+    with open(path, "w") as fh:
+        json.dump(doc, fh)
+    return path
 
 
 def case_setup(name):

@@ -352,6 +352,24 @@ def test_plateau_curvature_circular_track(tmp_path, veh, spline):
         ev.close()
 
 
+@pytest.mark.parametrize("veh", ["tbr18", "mx5"])
+@pytest.mark.parametrize("spline,tol", [("fitpack", 5e-10), ("tridiagonal", 5e-9)])
+def test_plateau_circle_against_unmodified_reference(tmp_path, veh, spline, tol):
+    """The same plateau candidates against lap times of the unmodified reference (tests/golden/plateau_circle.npz)."""
+    from conftest import GOLDEN_DIR, circle_track_json
+
+    g = dict(np.load(os.path.join(GOLDEN_DIR, "plateau_circle.npz")))
+    tj = circle_track_json(tmp_path, g)
+    vj = ltk.data_path("vehicles", "MX5.json" if veh == "mx5" else "tbr18.json")
+    for mode in ("bayes", "full"):
+        ev = ltk.LapTimeEvaluator(ltk.Track(tj, track_width=float(g["width"]), quiet=True), ltk.load_vehicle(vj), mode, None,
+                                  spline=spline)
+        assert ev.ns == int(g[f"{veh}_{mode}_ns"])
+        got = ev.lap_times(g[f"{veh}_{mode}_alphas"])
+        ev.close()
+        assert rel_err(got, g[f"{veh}_{mode}_laps"]).max() <= tol, mode
+
+
 # ---- properties ----------------------------------------------------------------------------------------
 def test_idempotent_and_permutation_invariant(buckmore):
     ev, _ = buckmore

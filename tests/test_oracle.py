@@ -2,6 +2,8 @@
 (tools/make_golden.py).  Level 1 (Python port, same SciPy/numpy) must be bit-exact; level 2 (C, own
 periodic spline) must reproduce the sweeps bit-exactly when fed the reference curvature and the whole
 path to the documented noise floor ("Parity")."""
+import os
+
 import numpy as np
 import pytest
 
@@ -221,4 +223,26 @@ def test_reference_arithmetic_depends_on_numpy_dispatch():
     base = lap_times_baseline_dispatch(tj, width, vj, a, mode)
     rel = np.abs(host - base) / base
     assert rel.max() < 2e-8
+
+
+@pytest.mark.parametrize("veh", ["tbr18", "mx5"])
+@pytest.mark.parametrize("mode", ["bayes", "full"])
+def test_plateau_circle_port_equals_reference(tmp_path, veh, mode):
+    """Curvature plateaus (circular corridor, symmetric candidates; tools/make_golden_plateau.py ran the unmodified
+    reference): the port reproduces the reference's lap times bit for bit there too, the C oracle to tolerance."""
+    import lap_time_optimization_b200 as ltk
+    from conftest import GOLDEN_DIR, circle_track_json
+    from oracle import c_oracle
+    from oracle.reference_port import OracleEvaluator, OracleTrack, load_vehicle
+
+    g = dict(np.load(os.path.join(GOLDEN_DIR, "plateau_circle.npz")))
+    tj = circle_track_json(tmp_path, g)
+    vj = ltk.data_path("vehicles", "MX5.json" if veh == "mx5" else "tbr18.json")
+    a, laps = g[f"{veh}_{mode}_alphas"], g[f"{veh}_{mode}_laps"]
+    port = OracleEvaluator(OracleTrack(tj, float(g["width"])), load_vehicle(vj), mode)
+    got = np.array([port.lap_time(x) for x in a[:24]])
+    assert np.array_equal(got, laps[:24])
+    for spline, tol in (("fitpack", 5e-10), ("tridiagonal", 5e-9)):  # (golden = the reference on an AVX512 host: its own pow noise)
+        co = c_oracle.COracle(OracleTrack(tj, float(g["width"])), load_vehicle(vj), mode, None, spline=spline)
+        assert rel_err(co.lap_times(a), laps).max() <= tol, spline
 
