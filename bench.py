@@ -688,7 +688,11 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
             "dtype": "f64" if args.sweep_bits == 64 else "f32 sweeps on f64 spline/curvature", "data": "synthetic",
-            "config": workload_config(args, na, ns),
+            "config": dict(workload_config(args, na, ns),
+                           kernels_per_step="k1a_solve, k1b_samples, k23_sweep (lap sum + top-10 in its epilogue)" +
+                                            (" + topk_merge_gathered after the all-gather" if world > 1 else ""),
+                           collective=("one all_gather of each rank's packed top-10 list (160 B) + one merge launch, on a "
+                                       "communication stream" if world > 1 else "none")),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * na * 8,
                     "d2h_bytes_per_step": B * 8 + TOPK * 16,
