@@ -33,10 +33,13 @@
 namespace ltk {
 
 constexpr int FUSED_THREADS = 64;
-constexpr int FUSED_UNROLL = 2;
+#ifndef LTK_FUSED_UNROLL
+#define LTK_FUSED_UNROLL 2  // row pairs per block of the regular path (A/B: 3, 4 -- more registers, fewer block headers)
+#endif
+constexpr int FUSED_UNROLL = LTK_FUSED_UNROLL;
 // bytes of readable memory the workspace keeps in front of the curvature array (ws_layout): the look-ahead
 // loads of the sweep run 2 * FUSED_UNROLL rows past the rows a chain uses, unconditionally
-constexpr size_t SWEEP_SLACK = 1024;
+constexpr size_t SWEEP_SLACK = 4096;
 #ifndef LTK_SWEEP_PREFETCH
 #define LTK_SWEEP_PREFETCH 2  // blocks of FUSED_UNROLL rows fetched into L1 ahead of the register look-ahead (0: none)
 #endif
