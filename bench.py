@@ -277,9 +277,11 @@ def fp64_pipe_model(args, B, n, ms_per_step, clocks):
 def issue_model(args, B, n, ms_per_step, clocks):
     """Issue-slot occupancy of one step under the cost model of DESIGN.md section 3 ("What binds"): one cycle per
     instruction, two per FP64 instruction, three per DFMA with three distinct register operands (tools/ubench), applied
-    to the SASS instruction counts of the kernels' loops.  Cycles per sample and warp: K23 277 (a block of two row pairs =
-    319 instructions, 160 FP64, 76 three-operand DFMAs = 555 cycles), K1b 135 (sample loop 88, interval switches 7,
-    write-out 10, per-CTA phases 30), K1a 20.  fp64 sweeps only; this is the builder's model, not a counter."""
+    to the SASS instruction counts of the kernels' loops (`python tools/issue_model.py lap_time_optimization_b200/libltk.so
+    <kernel>` prints them).  Cycles per sample and warp: K23 277 (two row pairs: phase 1 = a 261-instruction block with 160
+    FP64 and 12 three-operand DFMAs + the ~60-cycle loop header = 493 cycles, phase 2 = 315 / 200 / 20 + ~72 = 607; mean 550),
+    K1b 135 (sample loop 90 = 50 instructions, 30 FP64, 10 three-operand DFMAs; interval switches 7, write-out 10, per-CTA
+    phases 28), K1a 20.  fp64 sweeps only; this is the builder's model, not a counter."""
     if args.sweep_bits != 64 or args.spline != "tridiagonal":
         return None
     per_sample = 277 + 135 + 20
